@@ -1,0 +1,161 @@
+/*
+ * smoke_b200.h -- C ABI of libsmoke_sm100.so: the B200 (sm_100a) implementation of SmokePhysAI's
+ * grid smoke step (reference: src/physics/navier_stokes.py, smoke_simulator.py, fractal_generator.py).
+ *
+ * The reference has no FFI / plugin interface: its boundary is the Python class surface
+ * (SURVEY.md s8b).  This header is the boundary one level below it -- what the Python classes in
+ * smokephysai_b200/ bind with ctypes, and what any other host language would bind instead.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host
+ *   - the caller owns all memory; the library never allocates, frees or keeps a pointer after a call
+ *   - every entry point returns 0 on success, else a negative SMK_E* code or a positive cudaError_t;
+ *     smk_last_error_string() (thread-local) describes the last failure; nothing throws or exits
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no hidden syncs
+ *   - fields are fp32, row-major [row=y][col=x] with an element pitch that is a multiple of 4 and a
+ *     16-byte aligned base (float4 access); `batch` independent simulations are `stride_*` elements apart
+ *   - arithmetic follows the reference's fp32 association with no FMA contraction (built -fmad=false),
+ *     true division for /dt, so results are bit-identical to the reference's CPU path
+ */
+#ifndef SMOKE_B200_H
+#define SMOKE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMK_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SMK_API __attribute__((visibility("default")))
+#else
+#define SMK_API
+#endif
+
+enum {
+    SMK_OK = 0,
+    SMK_EINVAL = -1,      /* null pointer, bad dimension, bad pitch/alignment */
+    SMK_EUNSUPPORTED = -2 /* configuration outside what the kernels handle */
+};
+
+/* Geometry of one (batched) simulation state.  navier_stokes.py:21-35:
+ *   u[h+1][w]  v[h][w+1]  p[h][w]  density[h][w]   (+ div[h][w], frames[h][w] share the p layout) */
+typedef struct smk_grid {
+    int32_t h, w;        /* cells: grid_size = (h, w)                           navier_stokes.py:21 */
+    int32_t batch;       /* independent simulations (1 for the reference's scalar API)            */
+    int32_t pitch_u;     /* elements between rows of u                                            */
+    int32_t pitch_v;     /* elements between rows of v                                            */
+    int32_t pitch_c;     /* elements between rows of p / density / div / frame                    */
+    int64_t stride_u;    /* elements between consecutive simulations' u                           */
+    int64_t stride_v;
+    int64_t stride_c;
+} smk_grid_t;
+
+/* One Gaussian emitter, add_smoke_source(x, y, radius, intensity): navier_stokes.py:37 */
+typedef struct smk_source {
+    int32_t x, y, radius;
+    float intensity;
+} smk_source_t;
+
+/* Whole-step state: ping-pong copies of every field; cur_* say which copy is live and are updated
+ * (on the host, in this struct) by smk_step / smk_run_steps. */
+typedef struct smk_state {
+    float* u[2];
+    float* v[2];
+    float* d[2];
+    float* p[2];
+    float* div;
+    int32_t cur_u, cur_v, cur_d, cur_p;
+} smk_state_t;
+
+/* Scalar coefficients, pre-rounded on the host exactly as the reference's Python does:
+ *   dt    = float32(self.dt)
+ *   c_uv  = float32(self.dt * self.viscosity)            navier_stokes.py:72 via :158-159
+ *   c_d   = float32(self.dt * (self.viscosity * 0.1))    navier_stokes.py:72 via :160
+ *   decay = 0.995f                                       navier_stokes.py:171                   */
+typedef struct smk_params {
+    float dt, c_uv, c_d, decay;
+    int32_t jacobi_iters;       /* 20 in the reference (navier_stokes.py:139)                      */
+    int32_t sweeps_per_launch;  /* temporal-blocking depth T; 0 = library default                  */
+} smk_params_t;
+
+SMK_API int smk_version(void);
+SMK_API const char* smk_last_error_string(void);
+/* sm_count, compute capability major*10+minor and max opt-in shared memory of the current device */
+SMK_API int smk_device_info(int32_t* sm_count, int32_t* cc, int32_t* smem_optin);
+/* number of kernels this library has launched in this process so far (monotonic, all threads) */
+SMK_API int smk_launch_count(int64_t* count);
+/* make `device` current for this thread inside the library's (statically linked) CUDA runtime */
+SMK_API int smk_set_device(int32_t device);
+
+/* a2  add_smoke_source (navier_stokes.py:37-48), batched: simulation b applies sources
+ *     [offsets[b], offsets[b+1]) in list order (order matters where emitters overlap). */
+SMK_API int smk_splat_sources(const smk_grid_t* g, float* density, const smk_source_t* sources,
+                      const int32_t* offsets, void* stream);
+
+/* a4  diffusion_step (navier_stokes.py:50-72) on one field [batch][rows][cols]; c = float32(dt*viscosity) */
+SMK_API int smk_diffuse(const float* in, float* out, int32_t rows, int32_t cols, int32_t pitch,
+                int32_t batch, int64_t stride, float c, void* stream);
+
+/* a3+a4+a5 fused: buoyancy (:154-155), the three diffusions (:158-160) and the divergence (:136)
+ *     in one pass; div may be NULL. */
+SMK_API int smk_forces_diffuse_div(const smk_grid_t* g, const float* u, const float* v, const float* d,
+                           float* u_out, float* v_out, float* d_out, float* div,
+                           float dt, float c_uv, float c_d, void* stream);
+
+/* a5  divergence alone (navier_stokes.py:136) */
+SMK_API int smk_divergence(const smk_grid_t* g, const float* u, const float* v, float* div, float dt, void* stream);
+
+/* a6  K Jacobi sweeps (navier_stokes.py:139-145), T sweeps fused per launch (temporal blocking, pressure
+ *     tile held in registers).  Ping-pongs between p and p_scratch; *result_in_scratch tells where the
+ *     final field is.  T = 0 picks the default. */
+SMK_API int smk_jacobi(const smk_grid_t* g, const float* div, float* p, float* p_scratch,
+               int32_t K, int32_t T, int32_t* result_in_scratch_host, void* stream);
+
+/* a7  gradient subtract in place (navier_stokes.py:148-149) */
+SMK_API int smk_project(const smk_grid_t* g, const float* p, float* u, float* v, float dt, void* stream);
+
+/* a8  bilinear_interpolate (navier_stokes.py:111-131) at n arbitrary (y, x); mode 0 plain,
+ *     1 = interpolate_velocity_u (x+0.5 clamped, :97-102), 2 = interpolate_velocity_v (y+0.5 clamped, :104-109) */
+SMK_API int smk_bilerp(const float* field, int32_t rows, int32_t cols, int32_t pitch,
+               const float* y, const float* x, float* out, int64_t n, int32_t mode, void* stream);
+
+/* a10 advection_step (navier_stokes.py:74-95) of one field [batch][rows][cols] by (u, v) of grid g.
+ *     scale != 1 multiplies the result (the 0.995 decay of :171); frame (may be NULL) receives
+ *     out + fmul*out when fmul != NULL (fractal_generator.py:62) else a copy of out (:173). */
+SMK_API int smk_advect(const smk_grid_t* g, const float* field, float* out, int32_t rows, int32_t cols,
+               int32_t pitch, int64_t stride, const float* u, const float* v, float dt,
+               float scale, float* frame, int64_t frame_stride, const float* fmul, void* stream);
+
+/* a3-a11 one full step() / n steps (navier_stokes.py:151-173) over the state.  frames (may be NULL):
+ *     [batch][nsteps][h][pitch_c] returned copies, multiplied by (1+fmul) when fmul != NULL. */
+SMK_API int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
+             float* frame, int64_t frame_stride, const float* fmul, void* stream);
+SMK_API int smk_run_steps(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, int32_t nsteps,
+                  float* frames, int64_t frame_step_stride, int64_t frame_batch_stride,
+                  const float* fmul, void* stream);
+
+/* diagnostics: per simulation {max|div|, sum div^2} of the un-normalised divergence of (u, v);
+ *     out[2*batch] must be zeroed by the caller; warp-shuffle + atomic reduction. */
+SMK_API int smk_div_norms(const smk_grid_t* g, const float* u, const float* v, float* out, void* stream);
+
+/* a13 FractalGenerator fields (fractal_generator.py:12-62).  Output index [a][b], a < na (= w), b < nb (= h),
+ *     as torch.meshgrid(x_w, y_h, indexing='ij') lays them out.  Any of the three outputs may be NULL:
+ *       perlin = (sum_o 0.5^o sin(2^o px[a]) cos(2^o py[b]) + 1) / 2                      (:12-31)
+ *       mandel = escape_count(z <- z^2 + mx[a] + i my[b], |z| <= 2) / iterations          (:33-51)
+ *       mul    = intensity * (0.7*perlin + 0.3*mandel)                                    (:59,:62)
+ *     px/py/mx/my are the torch.linspace grids, made on the host exactly as the reference makes them
+ *     (ATen's CPU linspace is ISA-dependent in the last ulp, and the escape count is sensitive to it). */
+SMK_API int smk_fractal_fields(float* perlin, float* mandel, float* mul, int32_t na, int32_t nb, int32_t pitch,
+                       float intensity, int32_t iterations,
+                       const float* px, const float* py, const float* mx, const float* my, void* stream);
+/* out = field + mul*field (fractal_generator.py:62) */
+SMK_API int smk_apply_mul(const float* field, const float* mul, float* out, int32_t rows, int32_t cols,
+                  int32_t pitch, int32_t batch, int64_t stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMOKE_B200_H */

@@ -1,0 +1,99 @@
+"""ctypes binding of libsmoke_sm100.so (the C ABI declared in include/smoke_b200.h).
+
+There is no fallback: if the shared object is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libsmoke_sm100.so")
+
+c_f, c_i32, c_i64, c_p = C.c_float, C.c_int32, C.c_int64, C.c_void_p
+
+
+class Grid(C.Structure):                     # smk_grid_t
+    _fields_ = [("h", c_i32), ("w", c_i32), ("batch", c_i32),
+                ("pitch_u", c_i32), ("pitch_v", c_i32), ("pitch_c", c_i32),
+                ("stride_u", c_i64), ("stride_v", c_i64), ("stride_c", c_i64)]
+
+
+class Source(C.Structure):                   # smk_source_t
+    _fields_ = [("x", c_i32), ("y", c_i32), ("radius", c_i32), ("intensity", c_f)]
+
+
+class State(C.Structure):                    # smk_state_t
+    _fields_ = [("u", c_p * 2), ("v", c_p * 2), ("d", c_p * 2), ("p", c_p * 2), ("div", c_p),
+                ("cur_u", c_i32), ("cur_v", c_i32), ("cur_d", c_i32), ("cur_p", c_i32)]
+
+
+class Params(C.Structure):                   # smk_params_t
+    _fields_ = [("dt", c_f), ("c_uv", c_f), ("c_d", c_f), ("decay", c_f),
+                ("jacobi_iters", c_i32), ("sweeps_per_launch", c_i32)]
+
+
+GP, SP, PP = C.POINTER(Grid), C.POINTER(State), C.POINTER(Params)
+
+# name -> argtypes; every function returns int except smk_last_error_string.  Kept in one table so
+# tests can check it against the header and the exported symbols.
+SIGNATURES = {
+    "smk_version": [],
+    "smk_device_info": [C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32)],
+    "smk_launch_count": [C.POINTER(c_i64)],
+    "smk_set_device": [c_i32],
+    "smk_splat_sources": [GP, c_p, c_p, c_p, c_p],
+    "smk_diffuse": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i64, c_f, c_p],
+    "smk_forces_diffuse_div": [GP, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_p],
+    "smk_divergence": [GP, c_p, c_p, c_p, c_f, c_p],
+    "smk_jacobi": [GP, c_p, c_p, c_p, c_i32, c_i32, C.POINTER(c_i32), c_p],
+    "smk_project": [GP, c_p, c_p, c_p, c_f, c_p],
+    "smk_bilerp": [c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i64, c_i32, c_p],
+    "smk_advect": [GP, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_f, c_f, c_p, c_i64, c_p, c_p],
+    "smk_step": [GP, SP, PP, c_p, c_i64, c_p, c_p],
+    "smk_run_steps": [GP, SP, PP, c_i32, c_p, c_i64, c_i64, c_p, c_p],
+    "smk_div_norms": [GP, c_p, c_p, c_p, c_p],
+    "smk_fractal_fields": [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f, c_i32, c_p, c_p, c_p, c_p, c_p],
+    "smk_apply_mul": [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i64, c_p],
+}
+
+_lib = None
+
+
+class SmokeLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libsmoke_sm100.so (built by smokephysai_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise SmokeLibraryError(
+            "%s is missing: build it with `python -m smokephysai_b200.build` (nvcc, sm_100a). "
+            "There is no CPU or PyTorch fallback for the smoke step." % SO_PATH)
+    lib = C.CDLL(SO_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.smk_last_error_string.argtypes = []
+    lib.smk_last_error_string.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().smk_last_error_string()
+        raise SmokeLibraryError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)
+
+
+def launch_count():
+    """Kernels launched by the library in this process so far."""
+    n = c_i64(0)
+    call("smk_launch_count", C.byref(n))
+    return n.value

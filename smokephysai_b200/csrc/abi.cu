@@ -1,0 +1,236 @@
+// abi.cu -- the extern "C" surface of libsmoke_sm100.so (include/smoke_b200.h): argument validation,
+// thread-local error string, and the whole-step orchestration of navier_stokes.py:151-173.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include "common.cuh"
+
+namespace smk {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+    return SMK_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_grid(const smk_grid_t* g, const char* who)
+{
+    if (!g) return fail(SMK_EINVAL, "%s: grid is NULL", who);
+    if (g->h < 1 || g->w < 1) return fail(SMK_EINVAL, "%s: bad grid %d x %d", who, g->h, g->w);
+    if (g->batch < 1 || g->batch > 65535) return fail(SMK_EINVAL, "%s: batch %d outside [1, 65535]", who, g->batch);
+    if (g->pitch_u < g->w || g->pitch_c < g->w || g->pitch_v < g->w + 1)
+        return fail(SMK_EINVAL, "%s: pitch smaller than the row (u %d, v %d, c %d for w=%d)", who, g->pitch_u, g->pitch_v, g->pitch_c, g->w);
+    if ((g->pitch_u | g->pitch_v | g->pitch_c) & 3)
+        return fail(SMK_EINVAL, "%s: pitches must be multiples of 4 elements (u %d, v %d, c %d)", who, g->pitch_u, g->pitch_v, g->pitch_c);
+    if ((g->stride_u | g->stride_v | g->stride_c) & 3)
+        return fail(SMK_EINVAL, "%s: batch strides must be multiples of 4 elements", who);
+    if (g->batch > 1 && (g->stride_u < (int64_t)(g->h + 1) * g->pitch_u || g->stride_v < (int64_t)g->h * g->pitch_v ||
+                         g->stride_c < (int64_t)g->h * g->pitch_c))
+        return fail(SMK_EINVAL, "%s: batch stride smaller than one field", who);
+    return SMK_OK;
+}
+
+static int check_ptrs(const char* who, std::initializer_list<const void*> ps)
+{
+    int k = 0;
+    for (const void* p : ps) {
+        if (!p) return fail(SMK_EINVAL, "%s: pointer argument %d is NULL", who, k);
+        if (!aligned16(p)) return fail(SMK_EINVAL, "%s: pointer argument %d is not 16-byte aligned", who, k);
+        ++k;
+    }
+    return SMK_OK;
+}
+
+}  // namespace smk
+
+using namespace smk;
+
+#define SMK_TRY(x) do { const int rc_ = (x); if (rc_ != SMK_OK) return rc_; } while (0)
+
+extern "C" {
+
+int smk_version(void) { return SMK_ABI_VERSION; }
+
+const char* smk_last_error_string(void) { return g_err; }
+
+int smk_device_info(int32_t* sm_count, int32_t* cc, int32_t* smem_optin)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    cudaDeviceProp p;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) return fail((int)e, "smk_device_info: %s", cudaGetErrorString(e));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc) *cc = p.major * 10 + p.minor;
+    if (smem_optin) *smem_optin = (int32_t)p.sharedMemPerBlockOptin;
+    return SMK_OK;
+}
+
+int smk_launch_count(int64_t* count)
+{
+    if (!count) return fail(SMK_EINVAL, "smk_launch_count: NULL");
+    *count = g_launches.load(std::memory_order_relaxed);
+    return SMK_OK;
+}
+
+int smk_set_device(int32_t device)
+{
+    const cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail((int)e, "smk_set_device(%d): %s", device, cudaGetErrorString(e));
+    return SMK_OK;
+}
+
+int smk_splat_sources(const smk_grid_t* g, float* density, const smk_source_t* sources, const int32_t* offsets, void* stream)
+{
+    SMK_TRY(check_grid(g, "smk_splat_sources"));
+    SMK_TRY(check_ptrs("smk_splat_sources", {density}));
+    if (!sources || !offsets) return fail(SMK_EINVAL, "smk_splat_sources: sources/offsets NULL");
+    return launch_splat(g, density, sources, offsets, (cudaStream_t)stream);
+}
+
+int smk_diffuse(const float* in, float* out, int32_t rows, int32_t cols, int32_t pitch, int32_t batch, int64_t stride,
+                float c, void* stream)
+{
+    if (rows < 1 || cols < 1 || pitch < cols || batch < 1 || batch > 65535)
+        return fail(SMK_EINVAL, "smk_diffuse: bad shape %d x %d pitch %d batch %d", rows, cols, pitch, batch);
+    if (!in || !out || in == out) return fail(SMK_EINVAL, "smk_diffuse: in/out NULL or aliased (the stencil is out of place)");
+    return launch_diffuse(in, out, rows, cols, pitch, batch, stride, c, (cudaStream_t)stream);
+}
+
+int smk_forces_diffuse_div(const smk_grid_t* g, const float* u, const float* v, const float* d,
+                           float* u_out, float* v_out, float* d_out, float* div, float dt, float c_uv, float c_d, void* stream)
+{
+    SMK_TRY(check_grid(g, "smk_forces_diffuse_div"));
+    SMK_TRY(check_ptrs("smk_forces_diffuse_div", {u, v, d, u_out, v_out, d_out}));
+    if (u == u_out || v == v_out || d == d_out) return fail(SMK_EINVAL, "smk_forces_diffuse_div: outputs must not alias inputs");
+    if (!(dt != 0.0f)) return fail(SMK_EINVAL, "smk_forces_diffuse_div: dt must be non-zero");
+    return launch_forces_diffuse_div(g, u, v, d, u_out, v_out, d_out, div, dt, c_uv, c_d, (cudaStream_t)stream);
+}
+
+int smk_divergence(const smk_grid_t* g, const float* u, const float* v, float* div, float dt, void* stream)
+{
+    SMK_TRY(check_grid(g, "smk_divergence"));
+    SMK_TRY(check_ptrs("smk_divergence", {u, v, div}));
+    return launch_divergence(g, u, v, div, dt, (cudaStream_t)stream);
+}
+
+int smk_jacobi(const smk_grid_t* g, const float* div, float* p, float* p_scratch, int32_t K, int32_t T,
+               int32_t* result_in_scratch_host, void* stream)
+{
+    SMK_TRY(check_grid(g, "smk_jacobi"));
+    SMK_TRY(check_ptrs("smk_jacobi", {div, p, p_scratch}));
+    if (p == p_scratch) return fail(SMK_EINVAL, "smk_jacobi: p and p_scratch must differ");
+    if (K < 0 || T < 0) return fail(SMK_EINVAL, "smk_jacobi: negative K or T");
+    if (!result_in_scratch_host) return fail(SMK_EINVAL, "smk_jacobi: result_in_scratch_host is NULL");
+    int flag = 0;
+    const int rc = launch_jacobi(g, div, p, p_scratch, K, T, &flag, (cudaStream_t)stream);
+    *result_in_scratch_host = flag;
+    return rc;
+}
+
+int smk_project(const smk_grid_t* g, const float* p, float* u, float* v, float dt, void* stream)
+{
+    SMK_TRY(check_grid(g, "smk_project"));
+    SMK_TRY(check_ptrs("smk_project", {p, u, v}));
+    return launch_project(g, p, u, v, dt, (cudaStream_t)stream);
+}
+
+int smk_bilerp(const float* field, int32_t rows, int32_t cols, int32_t pitch, const float* y, const float* x,
+               float* out, int64_t n, int32_t mode, void* stream)
+{
+    if (!field || !y || !x || !out) return fail(SMK_EINVAL, "smk_bilerp: NULL pointer");
+    if (rows < 1 || cols < 1 || pitch < cols || n < 0 || mode < 0 || mode > 2)
+        return fail(SMK_EINVAL, "smk_bilerp: bad arguments (%d x %d pitch %d n %lld mode %d)", rows, cols, pitch, (long long)n, mode);
+    return launch_bilerp(field, rows, cols, pitch, y, x, out, n, mode, (cudaStream_t)stream);
+}
+
+int smk_advect(const smk_grid_t* g, const float* field, float* out, int32_t rows, int32_t cols, int32_t pitch, int64_t stride,
+               const float* u, const float* v, float dt, float scale, float* frame, int64_t frame_stride,
+               const float* fmul, void* stream)
+{
+    SMK_TRY(check_grid(g, "smk_advect"));
+    if (!field || !out || !u || !v) return fail(SMK_EINVAL, "smk_advect: NULL pointer");
+    if (field == out) return fail(SMK_EINVAL, "smk_advect: the gather is out of place, field == out");
+    if (out == u || out == v) return fail(SMK_EINVAL, "smk_advect: out aliases a velocity input");
+    if (rows < 1 || cols < 1 || pitch < cols) return fail(SMK_EINVAL, "smk_advect: bad field shape %d x %d pitch %d", rows, cols, pitch);
+    if (frame && (rows != g->h || cols != g->w)) return fail(SMK_EINVAL, "smk_advect: frame output needs a cell-centred field");
+    return launch_advect(g, field, out, rows, cols, pitch, stride, u, v, dt, scale, frame, frame_stride, fmul, (cudaStream_t)stream);
+}
+
+int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, float* frame, int64_t frame_stride,
+             const float* fmul, void* stream)
+{
+    SMK_TRY(check_grid(g, "smk_step"));
+    if (!st || !prm) return fail(SMK_EINVAL, "smk_step: state/params NULL");
+    SMK_TRY(check_ptrs("smk_step", {st->u[0], st->u[1], st->v[0], st->v[1], st->d[0], st->d[1], st->p[0], st->p[1], st->div}));
+    if ((st->cur_u | st->cur_v | st->cur_d | st->cur_p) & ~1) return fail(SMK_EINVAL, "smk_step: cur_* must be 0 or 1");
+    if (prm->jacobi_iters < 0) return fail(SMK_EINVAL, "smk_step: negative jacobi_iters");
+    if (!(prm->dt != 0.0f)) return fail(SMK_EINVAL, "smk_step: dt must be non-zero");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int cu = st->cur_u, cv = st->cur_v, cd = st->cur_d;
+    float *u0 = st->u[cu], *u1 = st->u[cu ^ 1], *v0 = st->v[cv], *v1 = st->v[cv ^ 1], *d0 = st->d[cd], *d1 = st->d[cd ^ 1];
+    // 1-2. buoyancy + diffusion + divergence                                   navier_stokes.py:154-160, :136
+    SMK_TRY(launch_forces_diffuse_div(g, u0, v0, d0, u1, v1, d1, st->div, prm->dt, prm->c_uv, prm->c_d, s));
+    // 3. Jacobi sweeps + gradient subtract                                     :139-149
+    int flip = 0;
+    SMK_TRY(launch_jacobi(g, st->div, st->p[st->cur_p], st->p[st->cur_p ^ 1], prm->jacobi_iters, prm->sweeps_per_launch, &flip, s));
+    st->cur_p ^= flip;
+    SMK_TRY(launch_project(g, st->p[st->cur_p], u1, v1, prm->dt, s));
+    // 4. sequential advection: u, then v with the new u, then density with both :166-168; 5. decay :171; copy :173
+    SMK_TRY(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, g->stride_u, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, s));
+    SMK_TRY(launch_advect(g, v1, v0, g->h, g->w + 1, g->pitch_v, g->stride_v, u0, v1, prm->dt, 1.0f, nullptr, 0, nullptr, s));
+    SMK_TRY(launch_advect(g, d1, d0, g->h, g->w, g->pitch_c, g->stride_c, u0, v0, prm->dt, prm->decay, frame, frame_stride, fmul, s));
+    return SMK_OK;
+}
+
+int smk_run_steps(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, int32_t nsteps,
+                  float* frames, int64_t frame_step_stride, int64_t frame_batch_stride, const float* fmul, void* stream)
+{
+    if (nsteps < 0) return fail(SMK_EINVAL, "smk_run_steps: negative nsteps");
+    for (int t = 0; t < nsteps; ++t)
+        SMK_TRY(smk_step(g, st, prm, frames ? frames + (int64_t)t * frame_step_stride : nullptr, frame_batch_stride, fmul, stream));
+    return SMK_OK;
+}
+
+int smk_div_norms(const smk_grid_t* g, const float* u, const float* v, float* out, void* stream)
+{
+    SMK_TRY(check_grid(g, "smk_div_norms"));
+    SMK_TRY(check_ptrs("smk_div_norms", {u, v}));
+    if (!out) return fail(SMK_EINVAL, "smk_div_norms: out NULL");
+    return launch_div_norms(g, u, v, out, (cudaStream_t)stream);
+}
+
+int smk_fractal_fields(float* perlin, float* mandel, float* mul, int32_t na, int32_t nb, int32_t pitch, float intensity,
+                       int32_t iterations, const float* px, const float* py, const float* mx, const float* my, void* stream)
+{
+    if (!perlin && !mandel && !mul) return fail(SMK_EINVAL, "smk_fractal_fields: no output requested");
+    if (((perlin || mul) && (!px || !py)) || ((mandel || mul) && (!mx || !my))) return fail(SMK_EINVAL, "smk_fractal_fields: NULL grid");
+    if (na < 1 || nb < 1 || pitch < nb || iterations < 1) return fail(SMK_EINVAL, "smk_fractal_fields: bad shape %d x %d pitch %d", na, nb, pitch);
+    return launch_fractal_fields(perlin, mandel, mul, na, nb, pitch, intensity, iterations, px, py, mx, my, (cudaStream_t)stream);
+}
+
+int smk_apply_mul(const float* field, const float* mul, float* out, int32_t rows, int32_t cols, int32_t pitch,
+                  int32_t batch, int64_t stride, void* stream)
+{
+    if (!field || !mul || !out) return fail(SMK_EINVAL, "smk_apply_mul: NULL pointer");
+    if (rows < 1 || cols < 1 || pitch < cols || batch < 1 || batch > 65535) return fail(SMK_EINVAL, "smk_apply_mul: bad shape");
+    return launch_apply_mul(field, mul, out, rows, cols, pitch, batch, stride, (cudaStream_t)stream);
+}
+
+}  // extern "C"

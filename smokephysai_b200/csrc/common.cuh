@@ -1,0 +1,82 @@
+// common.cuh -- shared device helpers and the internal launcher prototypes of libsmoke_sm100.so.
+//
+// Arithmetic contract (SURVEY.md s8a "parity traps"): every fp32 operation is rounded once, in the
+// association the reference's torch expressions imply.  The library is compiled with -fmad=false, so
+// nvcc never contracts a*b+c; division is IEEE (-prec-div=true default).  Do not add fast-math flags.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/smoke_b200.h"
+
+namespace smk {
+
+__device__ __forceinline__ int clampi(int a, int lo, int hi) { return min(max(a, lo), hi); }
+// torch.clamp(x, lo, hi) == min(max(x, lo), hi)
+__device__ __forceinline__ float clampf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
+
+// a8: bilinear_interpolate (navier_stokes.py:111-131) with a sampler f(row, col) over a Hg x Wg field.
+// Corner indices are clamped AFTER the +1 (:116-123), weights come from the clamped corners (:125-128),
+// the sum is ((wa*f00 + wb*f01) + wc*f10) + wd*f11 (:130-131).
+template <class Sampler>
+__device__ __forceinline__ float bilerp(const Sampler& f, int Hg, int Wg, float y, float x)
+{
+    int x0 = (int)floorf(x), y0 = (int)floorf(y);
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = clampi(x0, 0, Wg - 1); x1 = clampi(x1, 0, Wg - 1);
+    y0 = clampi(y0, 0, Hg - 1); y1 = clampi(y1, 0, Hg - 1);
+    const float ax = (float)x1 - x, bx = x - (float)x0;
+    const float ay = (float)y1 - y, by = y - (float)y0;
+    const float wa = ax * ay, wb = bx * ay, wc = ax * by, wd = bx * by;
+    float s = wa * f(y0, x0) + wb * f(y0, x1);
+    s = s + wc * f(y1, x0);
+    s = s + wd * f(y1, x1);
+    return s;
+}
+
+// a9: interpolate_velocity_u at integer (i, j) (navier_stokes.py:97-102), closed form.
+// x = min(j+0.5, w-1): for j <= w-2 the weights are 0.5/0.5 along x; along y the weight pair is (1, 0)
+// unless i is U's last row, where the clamped y1 == y0 makes both 0.  The zero-weight terms only add +-0.
+template <class Sampler>
+__device__ __forceinline__ float interp_u_at(const Sampler& U, int h, int w, int i, int j)
+{
+    if (j > w - 2 || i > h - 1) return 0.0f;       // U has h+1 rows: last row index is h
+    return 0.5f * U(i, j) + 0.5f * U(i, j + 1);
+}
+// interpolate_velocity_v at integer (i, j) (navier_stokes.py:104-109): 0.5*(V[i][j] + V[i+1][j]) for
+// i <= h-2 and j <= w-1 (V has w+1 columns), else 0.
+template <class Sampler>
+__device__ __forceinline__ float interp_v_at(const Sampler& V, int h, int w, int i, int j)
+{
+    if (i > h - 2 || j > w - 1) return 0.0f;
+    return 0.5f * V(i, j) + 0.5f * V(i + 1, j);
+}
+
+struct GlobalField {
+    const float* __restrict__ p; int pitch;
+    __device__ __forceinline__ float operator()(int i, int j) const { return __ldg(p + (size_t)i * pitch + j); }
+};
+
+// thread-local error string + checks (abi.cu)
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+bool aligned16(const void* p);
+int check_grid(const smk_grid_t* g, const char* who);
+
+// launchers (one per kernel family); all asynchronous on `s`
+int launch_splat(const smk_grid_t* g, float* density, const smk_source_t* src, const int32_t* off, cudaStream_t s);
+int launch_diffuse(const float* in, float* out, int rows, int cols, int pitch, int batch, int64_t stride, float c, cudaStream_t s);
+int launch_forces_diffuse_div(const smk_grid_t* g, const float* u, const float* v, const float* d,
+                              float* uo, float* vo, float* dout, float* div, float dt, float c_uv, float c_d, cudaStream_t s);
+int launch_divergence(const smk_grid_t* g, const float* u, const float* v, float* div, float dt, cudaStream_t s);
+int launch_jacobi(const smk_grid_t* g, const float* div, float* p, float* scratch, int K, int T, int* in_scratch, cudaStream_t s);
+int launch_project(const smk_grid_t* g, const float* p, float* u, float* v, float dt, cudaStream_t s);
+int launch_bilerp(const float* f, int rows, int cols, int pitch, const float* y, const float* x, float* out, int64_t n, int mode, cudaStream_t s);
+int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows, int cols, int pitch, int64_t stride,
+                  const float* u, const float* v, float dt, float scale, float* frame, int64_t frame_stride,
+                  const float* fmul, cudaStream_t s);
+int launch_div_norms(const smk_grid_t* g, const float* u, const float* v, float* out, cudaStream_t s);
+int launch_fractal_fields(float* perlin, float* mandel, float* mul, int na, int nb, int pitch, float intensity, int iterations,
+                          const float* px, const float* py, const float* mx, const float* my, cudaStream_t s);
+int launch_apply_mul(const float* f, const float* mul, float* out, int rows, int cols, int pitch, int batch, int64_t stride, cudaStream_t s);
+
+}  // namespace smk

@@ -1,0 +1,156 @@
+// jacobi.cu -- a6: the Jacobi pressure sweeps of pressure_projection (navier_stokes.py:139-145).
+//
+//   K times:  p' = 0 ;  p'[i][j] = 0.25 * ((((p[i-1][j] + p[i+1][j]) + p[i][j-1]) + p[i][j+1]) - div[i][j])
+//             for 1 <= i <= h-2, 1 <= j <= w-2 ;  p = p'
+//
+// Design (B200): the pressure tile lives in REGISTERS for T fused sweeps (temporal blocking).  A warp
+// spans 128 columns (lane l owns columns 4l..4l+3 as a float4) and R consecutive rows; a CTA stacks NW
+// warps, i.e. a (NW*R) x 128 tile.  Per sweep a thread needs, from outside its registers, only
+//   - the column to its left / right: one __shfl_up / __shfl_down per row,
+//   - the row above its first / below its last row: one float4 through a double-buffered shared-memory
+//     halo line per warp, one __syncthreads per sweep.
+// div is loop-invariant and stays in registers too.  HBM/L2 traffic per launch is one read of p and div
+// and one write of p for T sweeps: 12/T B per cell-sweep (+ the overlap redundancy) instead of 12.
+// Tiles overlap by T rows and HX = roundup4(T) columns (trapezoid scheme: the outer ring of a tile goes
+// stale by one cell per sweep and is not stored); a grid that fits one tile needs no halo and does all K
+// sweeps in a single launch.  The Dirichlet ring and everything outside the domain is handled with a
+// per-cell multiplier (0.25 inside, 0 on the ring/outside), which costs no extra instruction.
+//
+// Bit-exactness: the association above is kept literally; 0.25*x == x*0.25 in IEEE; no FMA (-fmad=false).
+#include "common.cuh"
+
+namespace smk {
+
+template <int R, bool FAST>
+__device__ __forceinline__ void sweep_rows(float4 (&P)[R], const float4 (&D)[R], float4 up, const float4 dnh,
+                                           const float cm0, const float cm1, const float cm2, const float cm3,
+                                           const int gi0, const int h)
+{
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float4 cur = P[r];
+        const float4 dn = (r < R - 1) ? P[r + 1] : dnh;
+        const float left = __shfl_up_sync(0xffffffffu, cur.w, 1);
+        const float right = __shfl_down_sync(0xffffffffu, cur.x, 1);
+        float m0 = cm0, m1 = cm1, m2 = cm2, m3 = cm3;
+        if (!FAST) {
+            const int gi = gi0 + r;
+            if (gi < 1 || gi > h - 2) { m0 = 0.f; m1 = 0.f; m2 = 0.f; m3 = 0.f; }
+        }
+        float4 nw;
+        nw.x = m0 * ((((up.x + dn.x) + left) + cur.y) - D[r].x);
+        nw.y = m1 * ((((up.y + dn.y) + cur.x) + cur.z) - D[r].y);
+        nw.z = m2 * ((((up.z + dn.z) + cur.y) + cur.w) - D[r].z);
+        nw.w = m3 * ((((up.w + dn.w) + cur.z) + right) - D[r].w);
+        P[r] = nw;
+        up = cur;
+    }
+}
+
+template <int R, int NW>
+__global__ void __launch_bounds__(NW * 32, (NW * 32 <= 256) ? 2 : 1)
+k_jacobi(const float* __restrict__ pin, float* __restrict__ pout, const float* __restrict__ div,
+         const int h, const int w, const int pitch, const long long bstride,
+         const int T, const int HX, const int ox, const int oy)
+{
+    __shared__ float4 halo[2][2][NW][32];          // [buffer][0: first row, 1: last row][warp][lane]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * ox, y0 = blockIdx.y * oy;
+    const int gj = x0 + lane * 4;
+    const int gi0 = y0 + warp * R;
+    const size_t boff = (size_t)blockIdx.z * (size_t)bstride;
+    pin += boff; pout += boff; div += boff;
+
+    float4 P[R], D[R];
+    const bool colin = gj < pitch;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int gi = gi0 + r;
+        if (colin && gi < h) {
+            P[r] = *reinterpret_cast<const float4*>(pin + (size_t)gi * pitch + gj);
+            D[r] = __ldg(reinterpret_cast<const float4*>(div + (size_t)gi * pitch + gj));
+        } else {
+            P[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            D[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    const float cm0 = (gj + 0 >= 1 && gj + 0 <= w - 2) ? 0.25f : 0.f;
+    const float cm1 = (gj + 1 >= 1 && gj + 1 <= w - 2) ? 0.25f : 0.f;
+    const float cm2 = (gj + 2 >= 1 && gj + 2 <= w - 2) ? 0.25f : 0.f;
+    const float cm3 = (gj + 3 >= 1 && gj + 3 <= w - 2) ? 0.25f : 0.f;
+    const bool fast = (gi0 >= 1) && (gi0 + R - 1 <= h - 2);     // warp-uniform: no ring row in this warp
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int s = 0; s < T; ++s) {
+        const int buf = s & 1;
+        halo[buf][0][warp][lane] = P[0];
+        halo[buf][1][warp][lane] = P[R - 1];
+        __syncthreads();
+        const float4 up = warp > 0 ? halo[buf][1][warp - 1][lane] : zero4;
+        const float4 dn = warp < NW - 1 ? halo[buf][0][warp + 1][lane] : zero4;
+        if (fast) sweep_rows<R, true>(P, D, up, dn, cm0, cm1, cm2, cm3, gi0, h);
+        else      sweep_rows<R, false>(P, D, up, dn, cm0, cm1, cm2, cm3, gi0, h);
+    }
+
+    // store the part of the tile that is still exact after T sweeps
+    const int vx0 = x0 + (blockIdx.x > 0 ? HX : 0);
+    const int vx1 = (blockIdx.x + 1 < gridDim.x) ? x0 + 128 - HX : pitch;
+    const int vy0 = y0 + (blockIdx.y > 0 ? T : 0);
+    const int vy1 = (blockIdx.y + 1 < gridDim.y) ? y0 + NW * R - T : h;
+    if (gj >= vx0 && gj < vx1 && gj < pitch) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int gi = gi0 + r;
+            if (gi >= vy0 && gi < vy1 && gi < h)
+                *reinterpret_cast<float4*>(pout + (size_t)gi * pitch + gj) = P[r];
+        }
+    }
+}
+
+static int ntiles(int n, int tile, int halo)
+{
+    // first tile starts at 0, tiles advance by tile-2*halo, last tile must reach n
+    if (n <= tile) return 1;
+    const int adv = tile - 2 * halo;
+    return (n - tile + adv - 1) / adv + 1;
+}
+
+template <int R, int NW>
+static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, int K, int T, int* in_scratch, cudaStream_t s)
+{
+    const int TH = R * NW;
+    const bool whole = (g->h <= TH) && (g->w <= 128);
+    float* src = a; float* dst = b;
+    int done = 0;
+    while (done < K) {
+        int t = whole ? (K - done) : min(T, K - done);
+        const int HX = (t + 3) & ~3;
+        const int nx = ntiles(g->w, 128, HX), ny = ntiles(g->h, TH, t);
+        dim3 grid(nx, ny, g->batch);
+        k_jacobi<R, NW><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c, (long long)g->stride_c,
+                                                 t, HX, 128 - 2 * HX, TH - 2 * t);
+        const int rc = check_launch("k_jacobi");
+        if (rc != SMK_OK) return rc;
+        float* tmp = src; src = dst; dst = tmp;
+        done += t;
+    }
+    *in_scratch = (src == b) ? 1 : 0;
+    return SMK_OK;
+}
+
+int launch_jacobi(const smk_grid_t* g, const float* div, float* p, float* scratch, int K, int T, int* in_scratch, cudaStream_t s)
+{
+    *in_scratch = 0;
+    if (K <= 0) return SMK_OK;
+    if (g->batch > 65535) return fail(SMK_EUNSUPPORTED, "smk_jacobi: batch %d > 65535", g->batch);
+    if (T <= 0) T = 8;
+    if (g->w <= 128 && g->h <= 32) return run_cfg<4, 8>(g, div, p, scratch, K, T, in_scratch, s);
+    if (g->w <= 128 && g->h <= 64) return run_cfg<8, 8>(g, div, p, scratch, K, T, in_scratch, s);
+    if (g->w <= 128 && g->h <= 128) return run_cfg<8, 16>(g, div, p, scratch, K, T, in_scratch, s);
+    // large grids: overlapped tiles.  T must leave a positive advance in both directions.
+    if (T > 24) T = 24;
+    return run_cfg<8, 16>(g, div, p, scratch, K, T, in_scratch, s);
+}
+
+}  // namespace smk

@@ -1,0 +1,385 @@
+"""Parity of the CUDA path (through the Python class surface and the C ABI beneath it) against the
+golden vectors generated from the reference and against the live CPU oracle.
+
+Bar: the whole step is +,-,*,/ ,floor, clamp and gathers, kept in the reference's
+association with no FMA, so every field must be BIT-EQUAL (numeric ==) to the reference's CPU result.
+The only tolerances are the two transcendental spots: expf in the emitter splat (<= 5e-7 normalised)
+and sinf/cosf in the Perlin octaves (<= 5e-7 absolute).  north_star's 1e-4 is therefore met with
+four orders of margin; the tests assert the tighter bound.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import assert_same, emitters_for_sequence, nerr, sha
+
+pytestmark = pytest.mark.gpu
+
+from smokephysai_b200 import FractalGenerator, NavierStokesSimulator, SmokeSimulator, _lib  # noqa: E402
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def make(h, w, dt=0.01, nu=0.001, K=20, **kw):
+    return NavierStokesSimulator((h, w), dt, nu, "cuda", jacobi_iters=K, **kw)
+
+
+# ------------------------------------------------------------------------------------------- unit hooks
+def test_units_diffusion(golden):
+    g = golden("units")
+    ns = make(20, 28)
+    for nm in ("u", "v", "d"):
+        out = ns.diffusion_step(T(g["diff_%s_in" % nm]), float(g["diff_%s_visc" % nm]))
+        assert_same(N(out), g["diff_%s_out" % nm], "diffusion " + nm)
+
+
+def test_units_bilerp_and_interp(golden):
+    g = golden("units")
+    ns = make(20, 28)
+    assert_same(N(ns.bilinear_interpolate(T(g["bil_f"]), T(g["bil_y"]), T(g["bil_x"]))), g["bil_out"], "bilerp")
+    Y, X = torch.meshgrid(torch.arange(20, dtype=torch.float32), torch.arange(28, dtype=torch.float32), indexing="ij")
+    assert_same(N(ns.interpolate_velocity_u(T(g["adv_u"]), Y, X)), g["interp_u_out"], "interp u")
+    assert_same(N(ns.interpolate_velocity_v(T(g["adv_v"]), Y, X)), g["interp_v_out"], "interp v")
+
+
+def test_units_advection(golden):
+    g = golden("units")
+    ns = make(20, 28)
+    u, v, d = T(g["adv_u"]), T(g["adv_v"]), T(g["adv_d"])
+    assert_same(N(ns.advection_step(u, u, v)), g["adv_u_out"], "advect u")
+    assert_same(N(ns.advection_step(v, u, v)), g["adv_v_out"], "advect v")
+    assert_same(N(ns.advection_step(d, u, v)), g["adv_d_out"], "advect d")
+
+
+@pytest.mark.parametrize("K", [20, 7])
+def test_units_projection(golden, K):
+    g = golden("units")
+    ns = make(20, 28, K=K)
+    for k in ("u", "v", "p"):
+        setattr(ns, k, T(g["proj%d_%s_in" % (K, k)]))
+    ns.pressure_projection()
+    for k in ("p", "u", "v"):
+        assert_same(N(getattr(ns, k)), g["proj%d_%s_out" % (K, k)], "projection " + k)
+
+
+def test_units_splat(golden):
+    g = golden("units")
+    ns = make(48, 40)
+    for x, y, r, i in g["splat_src"]:
+        ns.add_smoke_source(int(x), int(y), radius=int(r), intensity=float(i))
+    d = N(ns.density)
+    assert np.array_equal(d != 0, g["splat_out"] != 0)
+    assert nerr(d, g["splat_out"]) < 5e-7
+
+
+# ------------------------------------------------------------------------------------- whole-step parity
+def test_small_random_steps(golden):
+    g = golden("small_random")
+    for tag in g["cases"]:
+        h, w, K, dt, nu = g["%s_meta" % tag]
+        ns = make(int(h), int(w), float(dt), float(nu), int(K))
+        for k in ("u", "v", "p", "density"):
+            setattr(ns, k, T(g["%s_0_%s" % (tag, k)]))
+        for t in (1, 2, 3):
+            frame = ns.step()
+            for k in ("u", "v", "p", "density"):
+                assert_same(N(getattr(ns, k)), g["%s_%d_%s" % (tag, t, k)], "case %s step %d %s" % (tag, t, k))
+            assert_same(N(frame), N(ns.density), "returned frame")
+            assert frame.data_ptr() != ns.density.data_ptr()
+
+
+@pytest.mark.parametrize("K", [20, 40, 100])
+def test_scenario_c1(golden, K):
+    """inference.py:40-41 emitters on the config.yaml grid (BASELINE config 1)."""
+    g = golden("scenario_c1")
+    ns = make(128, 128, K=K)
+    ns.density = T(g["density0"])
+    rows = {int(r[0]): (r, hs) for r, hs in zip(g["stats_K%d" % K], g["sha_K%d" % K])}
+    for t in range(1, 21):
+        ns.step()
+        if t in rows:
+            r, hs = rows[t]
+            got = [sha(N(getattr(ns, k))) for k in ("u", "v", "p", "density")]
+            assert got == list(hs), "K=%d t=%d sha mismatch" % (K, t)
+    if K == 20:
+        for k in ("u", "v", "p", "density"):
+            assert_same(N(getattr(ns, k)), g["final_" + k], k)
+
+
+def test_post_projection_divergence_norms(golden):
+    """smk_div_norms after pressure_projection matches the reference's residual (north_star: matching
+    post-projection divergence residual)."""
+    g = golden("scenario_c1")
+    ns = make(128, 128)
+    ns.density = T(g["density0"])
+    row = g["stats_K20"][0]        # t = 1
+    st = ns._state
+    prm = ns._params()
+    grid = C.byref(ns._grid)
+    s = ns._stream()
+    _lib.call("smk_forces_diffuse_div", grid, st.u[0], st.v[0], st.d[0], st.u[1], st.v[1], st.d[1], st.div,
+              prm.dt, prm.c_uv, prm.c_d, s)
+    st.cur_u = st.cur_v = st.cur_d = 1
+    flag = C.c_int32(0)
+    _lib.call("smk_jacobi", grid, st.div, st.p[0], st.p[1], 20, 0, C.byref(flag), s)
+    st.cur_p = flag.value
+    _lib.call("smk_project", grid, st.p[st.cur_p], st.u[1], st.v[1], prm.dt, s)
+    nrm = ns.divergence_norms()[0]
+    assert abs(float(nrm[0]) - row[6]) <= 1e-6 * row[6]
+    assert abs(float(nrm[1]) - row[7]) <= 1e-4 * row[7]      # fp32 atomics sum vs float64 reference sum
+
+
+def test_batch_k40(golden):
+    """BASELINE config 2 at reduced size: independent sequences, K=40, batched in one state."""
+    g = golden("batch_k40")
+    K, B, steps = (int(x) for x in g["meta"])
+    ns = make(128, 128, K=K, batch=B)
+    ns.density = T(np.stack([g["density0_%d" % s] for s in range(B)]))
+    frames = ns.run_steps(steps)
+    assert tuple(frames.shape) == (B, steps, 128, 128)
+    for s in range(B):
+        got = [sha(N(getattr(ns, k)[s])) for k in ("u", "v", "p", "density")]
+        assert got == list(g["sha"][s]), "sequence %d" % s
+    for k in ("u", "v", "p", "density"):
+        assert_same(N(getattr(ns, k)[3]), g["final3_" + k], k)
+    assert_same(N(frames[:, -1]), N(ns.density), "last frame")
+
+
+def test_batch_own_splat_matches_golden_support(golden):
+    g = golden("batch_k40")
+    B = int(g["meta"][1])
+    ns = make(128, 128, K=40, batch=B)
+    per = [[] for _ in range(B)]
+    for s, x, y, r, i in g["sources"]:
+        per[int(s)].append((int(x), int(y), int(r), float(i)))
+    ns.add_sources(per)
+    d = N(ns.density)
+    for s in range(B):
+        assert per[s] == [tuple(e) for e in emitters_for_sequence(s)]
+        assert nerr(d[s], g["density0_%d" % s]) < 5e-7
+
+
+@pytest.mark.parametrize("T_", [0, 1, 5, 8, 12, 24])
+def test_grid_k100_tiled_jacobi(golden, T_):
+    """BASELINE config 3 at reduced size (256x256, K=100): exercises the overlapped-tile temporal blocking."""
+    g = golden("grid_k100")
+    ns = make(256, 256, K=100, sweeps_per_launch=T_)
+    ns.density = T(g["density0"])
+    for t in range(3):
+        ns.step()
+        got = [sha(N(getattr(ns, k))) for k in ("u", "v", "p", "density")]
+        assert got == list(g["sha"][t]), "T=%d t=%d" % (T_, t)
+    assert_same(N(ns.p), g["final_p"], "p")
+
+
+# ----------------------------------------------------------------- live oracle: ragged / odd / edge sizes
+@pytest.mark.parametrize("h,w,K,T_", [
+    (1, 1, 3, 0), (2, 2, 5, 0), (3, 3, 4, 0), (5, 131, 9, 4), (131, 5, 9, 4), (129, 129, 20, 8),
+    (130, 260, 17, 5), (300, 200, 33, 8), (257, 383, 20, 12), (64, 64, 20, 0), (33, 128, 20, 0), (100, 127, 40, 0),
+])
+def test_step_vs_oracle_ragged(h, w, K, T_):
+    rng = np.random.default_rng(h * 1000 + w)
+    ref = oracle.OracleSolver((h, w), 0.02, 0.01, K)
+    ref.u = ((rng.random((h + 1, w)) - 0.5) * 300).astype(np.float32)
+    ref.v = ((rng.random((h, w + 1)) - 0.5) * 300).astype(np.float32)
+    ref.p = rng.standard_normal((h, w)).astype(np.float32)
+    ref.density = rng.random((h, w)).astype(np.float32)
+    ns = make(h, w, 0.02, 0.01, K, sweeps_per_launch=T_)
+    for k in ("u", "v", "p", "density"):
+        setattr(ns, k, T(getattr(ref, k)))
+    for t in range(2):
+        ref.step()
+        ns.step()
+        for k in ("u", "v", "p", "density"):
+            assert_same(N(getattr(ns, k)), getattr(ref, k), "%dx%d K=%d T=%d step %d %s" % (h, w, K, T_, t, k))
+
+
+@pytest.mark.parametrize("h,w,K,T_", [(128, 128, 40, 0), (200, 136, 10, 3), (512, 640, 24, 8)])
+def test_jacobi_abi_vs_oracle(h, w, K, T_):
+    """smk_jacobi directly through the C ABI on random p (non-zero ring) and div."""
+    rng = np.random.default_rng(5)
+    p = rng.standard_normal((h, w)).astype(np.float32)
+    div = rng.standard_normal((h, w)).astype(np.float32)
+    ns = make(h, w, K=K, sweeps_per_launch=T_)
+    ns.p = T(p)
+    ns._field("div").copy_(T(div))
+    st = ns._state
+    flag = C.c_int32(0)
+    _lib.call("smk_jacobi", C.byref(ns._grid), st.div, st.p[0], st.p[1], K, T_, C.byref(flag), ns._stream())
+    st.cur_p = flag.value
+    assert_same(N(ns.p), oracle.jacobi(p, div, K), "jacobi")
+
+
+def test_full_size_c3_vs_oracle():
+    """BASELINE config 3 at full size: one 1024x1024 grid, K=100, one emitter per 64x64 block; 2 steps vs the oracle."""
+    n, K = 1024, 100
+    rng = np.random.default_rng(3)
+    ref = oracle.OracleSolver((n, n), 0.01, 0.001, K)
+    ns = make(n, n, K=K)
+    src = []
+    for by in range(n // 64):
+        for bx in range(n // 64):
+            src.append((int(bx * 64 + rng.integers(8, 56)), int(by * 64 + rng.integers(8, 56)), 8, float(rng.uniform(0.5, 2.0))))
+    ns.add_sources([src])
+    ref.density = N(ns.density).copy()          # isolate expf: same initial density on both sides
+    for t in range(2):
+        ref.step()
+        ns.step()
+    for k in ("u", "v", "p", "density"):
+        assert_same(N(getattr(ns, k)), getattr(ref, k), "1024^2 K=100 " + k)
+
+
+def test_full_size_c2_properties():
+    """BASELINE config 2 at full size (256 x 128^2, K=40): batch result == each sequence run alone, and
+    sequence 0..3 == oracle after 20 steps."""
+    B, K, steps = 256, 40, 20
+    ns = make(128, 128, K=K, batch=B)
+    ems = [emitters_for_sequence(s) for s in range(B)]
+    ns.add_sources(ems)
+    d0 = N(ns.density).copy()
+    frames = ns.run_steps(steps)
+    u, v, p, d = (N(getattr(ns, k)) for k in ("u", "v", "p", "density"))
+    # vs oracle on a few sequences (same initial density)
+    sel = [0, 1, 2, 3, 100, 255]
+    ou = np.zeros((len(sel), 129, 128), np.float32); ov = np.zeros((len(sel), 128, 129), np.float32)
+    op = np.zeros((len(sel), 128, 128), np.float32); od = d0[sel].copy()
+    ofr = oracle.run_batch(ou, ov, op, od, 0.01, 0.001, K, steps, nthreads=4)
+    for n_, s in enumerate(sel):
+        assert_same(u[s], ou[n_], "u seq %d" % s); assert_same(v[s], ov[n_], "v seq %d" % s)
+        assert_same(p[s], op[n_], "p seq %d" % s); assert_same(d[s], od[n_], "d seq %d" % s)
+        assert_same(N(frames[s]), ofr[n_], "frames seq %d" % s)
+    # batch == alone
+    one = make(128, 128, K=K)
+    one.density = T(d0[77])
+    fr1 = one.run_steps(steps)
+    assert_same(N(fr1), N(frames[77]), "sequence 77 alone vs in batch")
+    # edge quirk at scale: last row / col of density are exactly zero, pressure ring is zero
+    assert not d[:, -1, :].any() and not d[:, :, -1].any()
+    assert not p[:, 0, :].any() and not p[:, -1, :].any() and not p[:, :, 0].any() and not p[:, :, -1].any()
+
+
+# --------------------------------------------------------------------------------------------- facade
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 200])
+def test_fractal_fields(golden, n):
+    g = golden("facade")
+    fg = FractalGenerator("cuda")
+    # pin the kernel with the golden linspace grids (ISA-independent), then check the host-made grids agree here
+    pitch = (n + 3) & ~3
+    outs = [torch.zeros(n, pitch, device="cuda") for _ in range(3)]
+    grids = [T(g["lin_p_%d" % n]), T(g["lin_mx_%d" % n]), T(g["lin_my_%d" % n])]
+    _lib.call("smk_fractal_fields", outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), n, n, pitch, 0.05, 100,
+              grids[0].data_ptr(), grids[0].data_ptr(), grids[1].data_ptr(), grids[2].data_ptr(), fg._stream())
+    perlin, mandel, mul = (N(o[:, :n]) for o in outs)
+    assert_same(np.rint(mandel * 100), g["mandel_count_%d" % n].astype(np.float32), "mandelbrot escape counts")
+    assert_same(mandel, g["mandel_%d" % n], "mandelbrot field")
+    assert np.abs(perlin - g["perlin_%d" % n]).max() < 5e-7
+    assert np.abs((1.0 + mul) - g["pert_%d" % n]).max() < 3e-7
+    # class surface
+    assert np.abs(N(fg.generate_perlin_noise((n, n))) - g["perlin_%d" % n]).max() < 2e-6
+    assert np.abs(N(fg.apply_fractal_perturbation(torch.ones(n, n), 0.05)) - g["pert_%d" % n]).max() < 2e-6
+    m = N(fg.generate_mandelbrot_field((n, n)))
+    assert (np.rint(m * 100) != g["mandel_count_%d" % n]).sum() <= 2     # host linspace ulps may move a razor-edge pixel
+
+
+def test_fractal_nonsquare_raises_like_reference():
+    sim = SmokeSimulator((96, 160), device="cuda")
+    sim.add_incense_source([(50, 40)], [1.0])
+    sim.simulate_step(add_fractal=False)            # the solver itself handles non-square grids
+    with pytest.raises(RuntimeError):
+        sim.simulate_step()                          # fractal field is (w, h): the reference fails to broadcast
+
+
+def test_facade_sequence(golden):
+    """inference.py:35-50: 20 simulate_step() frames, then add_fractal=False, then chaos features."""
+    g, c1 = golden("facade"), golden("scenario_c1")
+    sim = SmokeSimulator((128, 128), 0.01, 0.001, "cuda")
+    sim.ns_solver.setup_grid()
+    sim.add_incense_source([(64, 64), (32, 32), (96, 96)], [1.5, 1.0, 0.8])
+    assert nerr(N(sim.ns_solver.density), c1["density0"]) < 5e-7
+    sim.ns_solver.density = T(c1["density0"])
+    frames = [N(sim.simulate_step()) for _ in range(20)]
+    assert nerr(frames[0], g["frame_1"]) < 3e-7 and nerr(frames[-1], g["frame_20"]) < 3e-7
+    for t in range(20):
+        assert abs(float(frames[t].astype(np.float64).sum()) - g["frames_sum"][t]) < 1e-4
+    assert_same(N(sim.ns_solver.density), c1["final_density"], "solver state is not perturbed by the fractal multiply")
+    assert_same(N(sim.simulate_step(add_fractal=False)), g["nofractal_21"], "add_fractal=False")
+    assert len(sim.history) == int(g["history_len"]) == 21
+    feats = sim.get_chaos_features()
+    ref = g["chaos"]
+    assert abs(feats["lyapunov_exponent"] - ref[0]) < 1e-6
+    assert abs(feats["fractal_dimension"] - ref[1]) < 1e-9
+    assert abs(feats["entropy"] - ref[2]) < 1e-5
+
+
+def test_history_ring_and_reset():
+    sim = SmokeSimulator((32, 32), device="cuda")
+    sim.max_history = 5
+    sim.add_incense_source([(16, 16)], [1.0])
+    for _ in range(8):
+        sim.simulate_step()
+    assert len(sim.history) == 5
+    sim.ns_solver.setup_grid()
+    assert len(sim.history) == 5            # setup_grid() does not clear history
+    assert not N(sim.ns_solver.density).any() and not N(sim.ns_solver.p).any()
+    assert sim.get_chaos_features() == {}
+
+
+def test_generate_sequences_matches_loop():
+    """Batched back-end of data_loader.py:37-99 == the reference's per-sample loop through the scalar API."""
+    B, L = 5, 6
+    ems = [[((x, y), i) for x, y, _, i in emitters_for_sequence(s)] for s in range(B)]
+    bat = SmokeSimulator((128, 128), device="cuda", batch=B)
+    fr = N(bat.generate_sequences(ems, L))
+    one = SmokeSimulator((128, 128), device="cuda")
+    for s in range(B):
+        one.ns_solver.setup_grid()
+        one.add_incense_source([e[0] for e in ems[s]], [e[1] for e in ems[s]])
+        seq = np.stack([N(one.simulate_step()) for _ in range(L)])
+        assert_same(fr[s], seq, "sequence %d" % s)
+
+
+def test_device_cpu_returns_cpu_tensors():
+    sim = SmokeSimulator((32, 32), device="cpu")         # benchmark.py:260
+    sim.add_incense_source([(16, 16)], [1.0])
+    f = sim.simulate_step()
+    assert f.device.type == "cpu" and sim.ns_solver.density.device.type == "cpu"
+    gsim = SmokeSimulator((32, 32), device="cuda")
+    gsim.add_incense_source([(16, 16)], [1.0])
+    assert_same(N(gsim.simulate_step()), N(f), "cpu-returning and cuda-returning simulators agree")
+
+
+def test_inplace_field_edits_and_pickle():
+    import pickle
+    ns = make(16, 16)
+    ns.density[4:8, 4:8] += 1.0
+    ns.density *= 0.5
+    assert float(ns.density.sum()) == 8.0
+    fr = ns.step()
+    assert torch.equal(pickle.loads(pickle.dumps(fr.cpu())), fr.cpu())
+    with pytest.raises(ValueError):
+        ns.u = torch.zeros(3, 3)
+
+
+def test_abi_rejects_bad_arguments():
+    ns = make(16, 16)
+    lib = _lib.load()
+    g = ns._grid
+    st = ns._state
+    flag = C.c_int32(0)
+    assert lib.smk_jacobi(C.byref(g), st.div, st.p[0], st.p[0], 4, 0, C.byref(flag), None) == -1
+    assert b"differ" in lib.smk_last_error_string()
+    assert lib.smk_jacobi(None, st.div, st.p[0], st.p[1], 4, 0, C.byref(flag), None) == -1
+    assert lib.smk_project(C.byref(g), st.p[0] + 4, st.u[0], st.v[0], 0.01, None) == -1      # misaligned
+    bad = type(g)(16, 16, 1, 15, 20, 16, 0, 0, 0)
+    assert lib.smk_divergence(C.byref(bad), st.u[0], st.v[0], st.div, 0.01, None) == -1
+    with pytest.raises(_lib.SmokeLibraryError):
+        _lib.call("smk_diffuse", st.u[0], st.u[0], 4, 4, 4, 1, 16, 0.1, None)
