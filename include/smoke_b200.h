@@ -90,6 +90,17 @@ SMK_API int smk_launch_count(int64_t* count);
 /* make `device` current for this thread inside the library's (statically linked) CUDA runtime */
 SMK_API int smk_set_device(int32_t device);
 
+/* Per-kernel device timing, for bench.py's roofline line: while a profile is open every kernel the library
+ * launches is bracketed by a pair of CUDA events recorded on the launching stream.  smk_profile_end
+ * synchronises those events, adds the elapsed milliseconds and launch counts up per phase, and closes the
+ * profile.  Process-wide, not re-entrant; off by default (no events, no overhead). */
+enum {
+    SMK_PH_SPLAT = 0, SMK_PH_FORCES_DIFFUSE_DIV, SMK_PH_JACOBI, SMK_PH_PROJECT,
+    SMK_PH_ADVECT_U, SMK_PH_ADVECT_V, SMK_PH_ADVECT_D, SMK_PH_OTHER, SMK_PH_COUNT
+};
+SMK_API int smk_profile_begin(int32_t max_records);
+SMK_API int smk_profile_end(double* ms_per_phase_host, int64_t* launches_per_phase_host, int32_t nphases);
+
 /* a2  add_smoke_source (navier_stokes.py:37-48), batched: simulation b applies sources
  *     [offsets[b], offsets[b+1]) in list order (order matters where emitters overlap). */
 SMK_API int smk_splat_sources(const smk_grid_t* g, float* density, const smk_source_t* sources,

@@ -40,6 +40,8 @@ SIGNATURES = {
     "smk_device_info": [C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32)],
     "smk_launch_count": [C.POINTER(c_i64)],
     "smk_set_device": [c_i32],
+    "smk_profile_begin": [c_i32],
+    "smk_profile_end": [C.POINTER(C.c_double), C.POINTER(c_i64), c_i32],
     "smk_splat_sources": [GP, c_p, c_p, c_p, c_p],
     "smk_diffuse": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i64, c_f, c_p],
     "smk_forces_diffuse_div": [GP, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_p],
@@ -97,3 +99,19 @@ def launch_count():
     n = c_i64(0)
     call("smk_launch_count", C.byref(n))
     return n.value
+
+
+PHASES = ("splat", "forces_diffuse_div", "jacobi", "project", "advect_u", "advect_v", "advect_d", "other")
+
+
+def profile_begin(max_records=4096):
+    call("smk_profile_begin", int(max_records))
+
+
+def profile_end():
+    """-> {phase: (total_ms, launches)} of every kernel launched since profile_begin()."""
+    n = len(PHASES)
+    ms = (C.c_double * n)()
+    cnt = (c_i64 * n)()
+    call("smk_profile_end", ms, cnt, n)
+    return {PHASES[k]: (ms[k], cnt[k]) for k in range(n)}

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <vector>
 #include "common.cuh"
 
 namespace smk {
@@ -25,6 +26,27 @@ int check_launch(const char* what)
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
     return SMK_OK;
+}
+
+// ---- per-kernel event timing ---------------------------------------------------------------------------
+struct ProfRec { int phase; cudaEvent_t a, b; };
+static std::atomic<bool> g_prof_on{false};
+static std::vector<ProfRec> g_prof;          // records in use
+static std::vector<cudaEvent_t> g_prof_pool; // pre-created events (2 per record)
+static size_t g_prof_used = 0;
+
+void prof_mark(int phase, cudaStream_t s, bool stop)
+{
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    if (!stop) {
+        if (g_prof_used + 2 > g_prof_pool.size()) return;      // pool exhausted: later launches go untimed
+        ProfRec r{phase, g_prof_pool[g_prof_used], g_prof_pool[g_prof_used + 1]};
+        g_prof_used += 2;
+        cudaEventRecord(r.a, s);
+        g_prof.push_back(r);
+    } else if (!g_prof.empty() && g_prof.back().phase == phase) {
+        cudaEventRecord(g_prof.back().b, s);
+    }
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -93,6 +115,41 @@ int smk_set_device(int32_t device)
 {
     const cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail((int)e, "smk_set_device(%d): %s", device, cudaGetErrorString(e));
+    return SMK_OK;
+}
+
+int smk_profile_begin(int32_t max_records)
+{
+    if (max_records < 1 || max_records > (1 << 20)) return fail(SMK_EINVAL, "smk_profile_begin: max_records %d", max_records);
+    if (g_prof_on.load()) return fail(SMK_EINVAL, "smk_profile_begin: a profile is already open");
+    while (g_prof_pool.size() < 2 * (size_t)max_records) {
+        cudaEvent_t e;
+        const cudaError_t rc = cudaEventCreate(&e);
+        if (rc != cudaSuccess) return fail((int)rc, "smk_profile_begin: %s", cudaGetErrorString(rc));
+        g_prof_pool.push_back(e);
+    }
+    g_prof.clear();
+    g_prof.reserve(max_records);
+    g_prof_used = 0;
+    g_prof_on.store(true);
+    return SMK_OK;
+}
+
+int smk_profile_end(double* ms, int64_t* launches, int32_t nphases)
+{
+    if (!g_prof_on.load()) return fail(SMK_EINVAL, "smk_profile_end: no profile is open");
+    g_prof_on.store(false);
+    if (!ms || !launches || nphases < SMK_PH_COUNT) return fail(SMK_EINVAL, "smk_profile_end: need %d phase slots", SMK_PH_COUNT);
+    for (int k = 0; k < nphases; ++k) { ms[k] = 0.0; launches[k] = 0; }
+    for (const ProfRec& r : g_prof) {
+        cudaError_t rc = cudaEventSynchronize(r.b);
+        float t = 0.f;
+        if (rc == cudaSuccess) rc = cudaEventElapsedTime(&t, r.a, r.b);
+        if (rc != cudaSuccess) return fail((int)rc, "smk_profile_end: %s", cudaGetErrorString(rc));
+        ms[r.phase] += (double)t;
+        launches[r.phase] += 1;
+    }
+    g_prof.clear();
     return SMK_OK;
 }
 

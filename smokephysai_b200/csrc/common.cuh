@@ -59,6 +59,13 @@ struct GlobalField {
 // thread-local error string + checks (abi.cu)
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
+// optional per-kernel event timing (smk_profile_begin/end): one scope object around each launch
+void prof_mark(int phase, cudaStream_t s, bool stop);
+struct ProfScope {
+    int phase; cudaStream_t s;
+    ProfScope(int phase_, cudaStream_t s_) : phase(phase_), s(s_) { prof_mark(phase, s, false); }
+    ~ProfScope() { prof_mark(phase, s, true); }
+};
 bool aligned16(const void* p);
 int check_grid(const smk_grid_t* g, const char* who);
 

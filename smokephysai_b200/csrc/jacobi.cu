@@ -128,9 +128,13 @@ static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, in
         const int HX = (t + 3) & ~3;
         const int nx = ntiles(g->w, 128, HX), ny = ntiles(g->h, TH, t);
         dim3 grid(nx, ny, g->batch);
-        k_jacobi<R, NW><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c, (long long)g->stride_c,
-                                                 t, HX, 128 - 2 * HX, TH - 2 * t);
-        const int rc = check_launch("k_jacobi");
+        int rc;
+        {
+            ProfScope prof_(SMK_PH_JACOBI, s);
+            k_jacobi<R, NW><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c, (long long)g->stride_c,
+                                                     t, HX, 128 - 2 * HX, TH - 2 * t);
+            rc = check_launch("k_jacobi");
+        }
         if (rc != SMK_OK) return rc;
         float* tmp = src; src = dst; dst = tmp;
         done += t;

@@ -101,6 +101,7 @@ int launch_forces_diffuse_div(const smk_grid_t* g, const float* u, const float* 
                               float* uo, float* vo, float* dout, float* div, float dt, float c_uv, float c_d, cudaStream_t s)
 {
     dim3 grid((g->w + FTW - 1) / FTW, (g->h + FTH - 1) / FTH, g->batch);
+    ProfScope prof_(SMK_PH_FORCES_DIFFUSE_DIV, s);
     k_forces_diffuse_div<<<grid, FTHREADS, 0, s>>>(u, v, d, uo, vo, dout, div, g->h, g->w, g->pitch_u, g->pitch_v, g->pitch_c,
                                                    g->stride_u, g->stride_v, g->stride_c, dt, c_uv, c_d);
     return check_launch("k_forces_diffuse_div");
@@ -124,6 +125,7 @@ __global__ void k_diffuse(const float* __restrict__ F, float* __restrict__ O, co
 int launch_diffuse(const float* in, float* out, int rows, int cols, int pitch, int batch, int64_t stride, float c, cudaStream_t s)
 {
     dim3 grid((cols + 31) / 32, (rows + 7) / 8, batch), blk(32, 8);
+    ProfScope prof_(SMK_PH_OTHER, s);
     k_diffuse<<<grid, blk, 0, s>>>(in, out, rows, cols, pitch, stride, c);
     return check_launch("k_diffuse");
 }
@@ -146,6 +148,7 @@ __global__ void k_divergence(const float* __restrict__ U, const float* __restric
 int launch_divergence(const smk_grid_t* g, const float* u, const float* v, float* div, float dt, cudaStream_t s)
 {
     dim3 grid((g->w + 31) / 32, (g->h + 7) / 8, g->batch), blk(32, 8);
+    ProfScope prof_(SMK_PH_OTHER, s);
     k_divergence<<<grid, blk, 0, s>>>(u, v, div, g->h, g->w, g->pitch_u, g->pitch_v, g->pitch_c,
                                       g->stride_u, g->stride_v, g->stride_c, dt);
     return check_launch("k_divergence");
@@ -174,6 +177,7 @@ __global__ void k_project(const float* __restrict__ P, float* __restrict__ U, fl
 int launch_project(const smk_grid_t* g, const float* p, float* u, float* v, float dt, cudaStream_t s)
 {
     dim3 grid((g->w + 31) / 32, (g->h + 7) / 8, g->batch), blk(32, 8);
+    ProfScope prof_(SMK_PH_PROJECT, s);
     k_project<<<grid, blk, 0, s>>>(p, u, v, g->h, g->w, g->pitch_u, g->pitch_v, g->pitch_c,
                                    g->stride_u, g->stride_v, g->stride_c, dt);
     return check_launch("k_project");
@@ -196,6 +200,7 @@ __global__ void k_bilerp(const float* __restrict__ F, const int rows, const int 
 int launch_bilerp(const float* f, int rows, int cols, int pitch, const float* y, const float* x, float* out, int64_t n, int mode, cudaStream_t s)
 {
     if (n <= 0) return SMK_OK;
+    ProfScope prof_(SMK_PH_OTHER, s);
     k_bilerp<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f, rows, cols, pitch, y, x, out, n, mode);
     return check_launch("k_bilerp");
 }
@@ -233,6 +238,7 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
                   const float* fmul, cudaStream_t s)
 {
     dim3 grid((cols + 31) / 32, (rows + 7) / 8, g->batch), blk(32, 8);
+    ProfScope prof_(rows == g->h + 1 ? SMK_PH_ADVECT_U : (cols == g->w + 1 ? SMK_PH_ADVECT_V : SMK_PH_ADVECT_D), s);
     k_advect<<<grid, blk, 0, s>>>(field, out, rows, cols, pitch, stride, u, v, g->h, g->w, g->pitch_u, g->pitch_v,
                                   g->stride_u, g->stride_v, dt, scale != 1.0f ? 1 : 0, scale,
                                   frame, frame_stride, g->pitch_c, fmul);
@@ -267,6 +273,7 @@ __global__ void k_splat(float* __restrict__ Dn, const int h, const int w, const 
 int launch_splat(const smk_grid_t* g, float* density, const smk_source_t* src, const int32_t* off, cudaStream_t s)
 {
     dim3 grid((g->w + 31) / 32, (g->h + 7) / 8, g->batch), blk(32, 8);
+    ProfScope prof_(SMK_PH_SPLAT, s);
     k_splat<<<grid, blk, 0, s>>>(density, g->h, g->w, g->pitch_c, g->stride_c, src, off);
     return check_launch("k_splat");
 }
@@ -313,6 +320,7 @@ k_div_norms(const float* __restrict__ U, const float* __restrict__ V, float* __r
 int launch_div_norms(const smk_grid_t* g, const float* u, const float* v, float* out, cudaStream_t s)
 {
     dim3 grid((g->w + 255) / 256, min(g->h, 64), g->batch);
+    ProfScope prof_(SMK_PH_OTHER, s);
     k_div_norms<<<grid, 256, 0, s>>>(u, v, out, g->h, g->w, g->pitch_u, g->pitch_v, g->stride_u, g->stride_v);
     return check_launch("k_div_norms");
 }
@@ -369,6 +377,7 @@ int launch_fractal_fields(float* perlin, float* mandel, float* mul, int na, int 
                           const float* px, const float* py, const float* mx, const float* my, cudaStream_t s)
 {
     dim3 grid((nb + 31) / 32, (na + 7) / 8), blk(32, 8);
+    ProfScope prof_(SMK_PH_OTHER, s);
     k_fractal_fields<<<grid, blk, 0, s>>>(perlin, mandel, mul, na, nb, pitch, intensity, iterations, px, py, mx, my);
     return check_launch("k_fractal_fields");
 }
@@ -386,6 +395,7 @@ __global__ void k_apply_mul(const float* __restrict__ F, const float* __restrict
 int launch_apply_mul(const float* f, const float* mul, float* out, int rows, int cols, int pitch, int batch, int64_t stride, cudaStream_t s)
 {
     dim3 grid((cols + 31) / 32, (rows + 7) / 8, batch), blk(32, 8);
+    ProfScope prof_(SMK_PH_OTHER, s);
     k_apply_mul<<<grid, blk, 0, s>>>(f, mul, out, rows, cols, pitch, stride);
     return check_launch("k_apply_mul");
 }
