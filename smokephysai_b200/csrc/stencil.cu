@@ -8,9 +8,46 @@ namespace smk {
 
 // =====================================================================================================
 // a3 + a4 + a5 fused: buoyancy, three diffusions, divergence -- one read of (u, v, d), one write of
-// (u', v', d', div).  Tile FTH x FTW cells; halo 1 for the diffusion + 1 row of u' / col of v' for div.
+// (u', v', d', div).  A CTA owns FTH x 128 cells.  The tile (+1 halo, replicate-clamped at the domain
+// edge, buoyancy already added to v) is staged in shared memory with one LDG.128 + STS.128 per four cells;
+// every thread then produces four consecutive cells from LDS.128 rows and stores them with STG.128.  The
+// diffused u / v go to a second pair of tiles from which the divergence is formed.
+// Shared column c of a staged row holds global column j0 - 4 + c (the body starts 16-byte aligned at c = 4,
+// the halo columns j0-1, j0+128, j0+129 sit at c = 3, 132, 133).
 // =====================================================================================================
-constexpr int FTH = 16, FTW = 64, FTHREADS = 256;
+constexpr int FTH = 16, FTW = 128, FSP = 136, FTHREADS = 256;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// diffusion_step: f + c*((((up+down)+left)+right) - 4f)                             navier_stokes.py:69-72
+__device__ __forceinline__ float diff1(float f, float up, float dn, float l, float r, float c)
+{
+    float s = up + dn;
+    s = s + l;
+    s = s + r;
+    return f + c * (s - 4.0f * f);
+}
+__device__ __forceinline__ float4 diff4(const float* up_row, const float* cur_row, const float* dn_row, int c4, float c)
+{
+    const float4 up = lds4(up_row + c4), cur = lds4(cur_row + c4), dn = lds4(dn_row + c4);
+    const float l = cur_row[c4 - 1], r = cur_row[c4 + 4];
+    float4 o;
+    o.x = diff1(cur.x, up.x, dn.x, l, cur.y, c);
+    o.y = diff1(cur.y, up.y, dn.y, cur.x, cur.z, c);
+    o.z = diff1(cur.z, up.z, dn.z, cur.y, cur.w, c);
+    o.w = diff1(cur.w, up.w, dn.w, cur.z, r, c);
+    return o;
+}
+// store the first `n` (1..4) lanes of v at p (p is 16-byte aligned)
+__device__ __forceinline__ void st4_partial(float* p, const float4 v, int n)
+{
+    if (n >= 4) { st4(p, v); return; }
+    if (n > 0) p[0] = v.x;
+    if (n > 1) p[1] = v.y;
+    if (n > 2) p[2] = v.z;
+}
 
 __global__ void __launch_bounds__(FTHREADS)
 k_forces_diffuse_div(const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ D,
@@ -19,81 +56,103 @@ k_forces_diffuse_div(const float* __restrict__ U, const float* __restrict__ V, c
                      const long long su_, const long long sv_, const long long sc_,
                      const float dt, const float c_uv, const float c_d)
 {
-    __shared__ float su[FTH + 3][FTW + 2];     // u rows i0-1 .. i0+FTH+1, cols j0-1 .. j0+FTW   (replicate-clamped)
-    __shared__ float sv[FTH + 2][FTW + 3];     // v+buoyancy rows i0-1 .. i0+FTH, cols j0-1 .. j0+FTW+1
-    __shared__ float sd[FTH + 2][FTW + 3];     // d, same window as sv
-    __shared__ float su1[FTH + 1][FTW];        // diffused u, rows i0 .. i0+FTH
-    __shared__ float sv1[FTH][FTW + 1];        // diffused v, cols j0 .. j0+FTW
+    __shared__ __align__(16) float su[FTH + 3][FSP];     // u rows i0-1 .. i0+FTH+1
+    __shared__ __align__(16) float sv[FTH + 2][FSP];     // v + buoyancy, rows i0-1 .. i0+FTH
+    __shared__ __align__(16) float sd[FTH + 2][FSP];     // density, same rows
+    __shared__ __align__(16) float su1[FTH + 1][FTW];    // diffused u, rows i0 .. i0+FTH
+    __shared__ __align__(16) float sv1[FTH][FTW + 4];    // diffused v, cols j0 .. j0+128
 
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const int i0 = blockIdx.y * FTH, j0 = blockIdx.x * FTW;
     const size_t b = blockIdx.z;
     U += b * su_; Uo += b * su_; V += b * sv_; Vo += b * sv_; D += b * sc_; Do += b * sc_;
     if (DIV) DIV += b * sc_;
+    const int c0 = j0 + 4 * lane;                  // first global column of this lane's float4
+    const int c4 = 4 + 4 * lane;                   // its shared-memory column
 
-    for (int k = tid; k < (FTH + 3) * (FTW + 2); k += FTHREADS) {
-        const int r = k / (FTW + 2), c = k % (FTW + 2);
-        su[r][c] = __ldg(U + (size_t)clampi(i0 - 1 + r, 0, h) * pu + clampi(j0 - 1 + c, 0, w - 1));
-    }
-    for (int k = tid; k < (FTH + 2) * (FTW + 3); k += FTHREADS) {
-        const int r = k / (FTW + 3), c = k % (FTW + 3);
-        const int ci = clampi(i0 - 1 + r, 0, h - 1);
-        const int cjv = clampi(j0 - 1 + c, 0, w), cjd = min(cjv, w - 1);
-        const float dv = __ldg(D + (size_t)ci * pc + cjd);
-        float vv = __ldg(V + (size_t)ci * pv + cjv);
-        if (cjv < w) {                       // v[:, :-1] += dt * (density * 0.1)      navier_stokes.py:154-155
-            const float bu = dv * 0.1f;
-            vv = vv + dt * bu;
+    // ---- stage u ------------------------------------------------------------------------------------
+    for (int r = wp; r < FTH + 3; r += FTHREADS / 32) {
+        const float* row = U + (size_t)clampi(i0 - 1 + r, 0, h) * pu;
+        float4 x;
+        if (c0 + 3 < w) x = ld4(row + c0);
+        else {
+            x.x = __ldg(row + min(c0, w - 1)); x.y = __ldg(row + min(c0 + 1, w - 1));
+            x.z = __ldg(row + min(c0 + 2, w - 1)); x.w = __ldg(row + min(c0 + 3, w - 1));
         }
-        sv[r][c] = vv;
-        sd[r][c] = dv;
+        st4(&su[r][c4], x);
+        if (lane < 2) su[r][lane == 0 ? 3 : 132] = __ldg(row + clampi(lane == 0 ? j0 - 1 : j0 + 128, 0, w - 1));
+    }
+    // ---- stage v (+ buoyancy: v[:, :-1] += dt * (density * 0.1), navier_stokes.py:154-155) and density ----
+    for (int r = wp; r < FTH + 2; r += FTHREADS / 32) {
+        const int gi = clampi(i0 - 1 + r, 0, h - 1);
+        const float* vrow = V + (size_t)gi * pv;
+        const float* drow = D + (size_t)gi * pc;
+        float4 x, y;
+        if (c0 + 3 < w) {
+            x = ld4(vrow + c0); y = ld4(drow + c0);
+            x.x = x.x + dt * (y.x * 0.1f); x.y = x.y + dt * (y.y * 0.1f);
+            x.z = x.z + dt * (y.z * 0.1f); x.w = x.w + dt * (y.w * 0.1f);
+        } else {
+            float vv[4], dd[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int cjv = min(c0 + k, w), cjd = min(cjv, w - 1);
+                dd[k] = __ldg(drow + cjd);
+                vv[k] = __ldg(vrow + cjv);
+                if (cjv < w) vv[k] = vv[k] + dt * (dd[k] * 0.1f);
+            }
+            x = make_float4(vv[0], vv[1], vv[2], vv[3]); y = make_float4(dd[0], dd[1], dd[2], dd[3]);
+        }
+        st4(&sv[r][c4], x); st4(&sd[r][c4], y);
+        if (lane < 3) {
+            const int sc = lane == 0 ? 3 : 131 + lane;
+            const int cjv = clampi(lane == 0 ? j0 - 1 : j0 + 127 + lane, 0, w), cjd = min(cjv, w - 1);
+            const float dv = __ldg(drow + cjd);
+            float vv = __ldg(vrow + cjv);
+            if (cjv < w) vv = vv + dt * (dv * 0.1f);
+            sv[r][sc] = vv; sd[r][sc] = dv;
+        }
     }
     __syncthreads();
 
-    // diffusion_step: f + c*((((up+down)+left)+right) - 4f)                          navier_stokes.py:69-72
-    for (int k = tid; k < (FTH + 1) * FTW; k += FTHREADS) {
-        const int r = k / FTW, c = k % FTW;
-        const int i = i0 + r, j = j0 + c;
-        const float f = su[r + 1][c + 1];
-        float s = su[r][c + 1] + su[r + 2][c + 1];
-        s = s + su[r + 1][c];
-        s = s + su[r + 1][c + 2];
-        const float o = f + c_uv * (s - 4.0f * f);
-        su1[r][c] = o;
-        if (i <= h && j < w && (r < FTH || i == h)) Uo[(size_t)i * pu + j] = o;
+    // ---- diffusion ------------------------------------------------------------------------------------
+    for (int r = wp; r <= FTH; r += FTHREADS / 32) {                    // u rows i0 .. i0+FTH
+        const int i = i0 + r;
+        const float4 o = diff4(su[r], su[r + 1], su[r + 2], c4, c_uv);
+        st4(&su1[r][4 * lane], o);
+        if (i <= h && (r < FTH || i == h)) st4_partial(Uo + (size_t)i * pu + c0, o, w - c0);
     }
-    for (int k = tid; k < FTH * (FTW + 1); k += FTHREADS) {
-        const int r = k / (FTW + 1), c = k % (FTW + 1);
-        const int i = i0 + r, j = j0 + c;
-        const float f = sv[r + 1][c + 1];
-        float s = sv[r][c + 1] + sv[r + 2][c + 1];
-        s = s + sv[r + 1][c];
-        s = s + sv[r + 1][c + 2];
-        const float o = f + c_uv * (s - 4.0f * f);
-        sv1[r][c] = o;
-        if (i < h && j <= w && (c < FTW || j == w)) Vo[(size_t)i * pv + j] = o;
+    for (int r = wp; r < FTH; r += FTHREADS / 32) {                     // v and density rows i0 .. i0+FTH-1
+        const int i = i0 + r;
+        const float4 o = diff4(sv[r], sv[r + 1], sv[r + 2], c4, c_uv);
+        st4(&sv1[r][4 * lane], o);
+        const float4 q = diff4(sd[r], sd[r + 1], sd[r + 2], c4, c_d);
+        if (i < h) {
+            st4_partial(Vo + (size_t)i * pv + c0, o, w + 1 - c0);
+            st4_partial(Do + (size_t)i * pc + c0, q, w - c0);
+        }
     }
-    for (int k = tid; k < FTH * FTW; k += FTHREADS) {
-        const int r = k / FTW, c = k % FTW;
-        const int i = i0 + r, j = j0 + c;
-        const float f = sd[r + 1][c + 1];
-        float s = sd[r][c + 1] + sd[r + 2][c + 1];
-        s = s + sd[r + 1][c];
-        s = s + sd[r + 1][c + 2];
-        if (i < h && j < w) Do[(size_t)i * pc + j] = f + c_d * (s - 4.0f * f);
+    if (threadIdx.x < FTH) {                                            // v column j0+128 (the staggered extra column)
+        const int r = threadIdx.x, i = i0 + r;
+        const float o = diff1(sv[r + 1][132], sv[r][132], sv[r + 2][132], sv[r + 1][131], sv[r + 1][133], c_uv);
+        sv1[r][128] = o;
+        if (i < h && j0 + 128 == w) Vo[(size_t)i * pv + w] = o;
     }
     if (DIV == nullptr) return;
     __syncthreads();
-    // div = (((u[i+1][j] - u[i][j]) + v[i][j+1]) - v[i][j]) / dt                      navier_stokes.py:136
-    for (int k = tid; k < FTH * FTW; k += FTHREADS) {
-        const int r = k / FTW, c = k % FTW;
-        const int i = i0 + r, j = j0 + c;
-        if (i < h && j < w) {
-            float s = su1[r + 1][c] - su1[r][c];
-            s = s + sv1[r][c + 1];
-            s = s - sv1[r][c];
-            DIV[(size_t)i * pc + j] = s / dt;
-        }
+    // ---- div = (((u[i+1][j] - u[i][j]) + v[i][j+1]) - v[i][j]) / dt                    navier_stokes.py:136
+    for (int r = wp; r < FTH; r += FTHREADS / 32) {
+        const int i = i0 + r;
+        if (i >= h) break;
+        const float4 ua = lds4(&su1[r][4 * lane]), ub = lds4(&su1[r + 1][4 * lane]);
+        const float4 va = lds4(&sv1[r][4 * lane]);
+        const float vr = sv1[r][4 * lane + 4];
+        float4 o;
+        o.x = (((ub.x - ua.x) + va.y) - va.x) / dt;
+        o.y = (((ub.y - ua.y) + va.z) - va.y) / dt;
+        o.z = (((ub.z - ua.z) + va.w) - va.z) / dt;
+        o.w = (((ub.w - ua.w) + vr) - va.w) / dt;
+        st4_partial(DIV + (size_t)i * pc + c0, o, w - c0);
     }
 }
 
@@ -155,28 +214,62 @@ int launch_divergence(const smk_grid_t* g, const float* u, const float* v, float
 }
 
 // ---- a7: gradient subtract, in place (navier_stokes.py:148-149) -----------------------------------------
-__global__ void k_project(const float* __restrict__ P, float* __restrict__ U, float* __restrict__ V,
-                          const int h, const int w, const int pu, const int pv, const int pc,
-                          const long long su_, const long long sv_, const long long sc_, const float dt)
+// One thread per four consecutive cells of a row: LDG.128 of p (this row and the row above), u and v,
+// the pressure to the left of the group through a warp shuffle, STG.128 of u and v.
+__global__ void __launch_bounds__(256)
+k_project(const float* __restrict__ P, float* __restrict__ U, float* __restrict__ V,
+          const int h, const int w, const int pu, const int pv, const int pc,
+          const long long su_, const long long sv_, const long long sc_, const float dt)
 {
-    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
-    if (i >= h || j >= w) return;
+    const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4, i = blockIdx.y * 8 + threadIdx.y;
     const size_t b = blockIdx.z;
     P += b * sc_; U += b * su_; V += b * sv_;
-    const float pc0 = P[(size_t)i * pc + j];
-    if (i >= 1) {        // u[1:-1, :] -= dt * (p[1:, :] - p[:-1, :])
-        const float gr = pc0 - P[(size_t)(i - 1) * pc + j];
-        U[(size_t)i * pu + j] = U[(size_t)i * pu + j] - dt * gr;
+    const bool in = i < h && c0 < w;
+    float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool full = in && c0 + 3 < w;
+    const float* prow = P + (size_t)i * pc;
+    if (full) p4 = ld4(prow + c0);
+    else if (in) {
+        p4.x = prow[c0];
+        if (c0 + 1 < w) p4.y = prow[c0 + 1];
+        if (c0 + 2 < w) p4.z = prow[c0 + 2];
     }
-    if (j >= 1) {        // v[:, 1:-1] -= dt * (p[:, 1:] - p[:, :-1])
-        const float gr = pc0 - P[(size_t)i * pc + j - 1];
-        V[(size_t)i * pv + j] = V[(size_t)i * pv + j] - dt * gr;
+    float pl = __shfl_up_sync(0xffffffffu, p4.w, 1);
+    if (!in) return;
+    if (threadIdx.x == 0 && c0 > 0) pl = prow[c0 - 1];
+    const int n = w - c0;                                    // valid columns in this group (>= 1)
+    if (i >= 1) {        // u[1:-1, :] -= dt * (p[1:, :] - p[:-1, :])
+        const float* qrow = prow - pc;
+        float* urow = U + (size_t)i * pu + c0;
+        if (full) {
+            const float4 q4 = ld4(qrow + c0);
+            float4 u4 = *reinterpret_cast<const float4*>(urow);
+            u4.x = u4.x - dt * (p4.x - q4.x); u4.y = u4.y - dt * (p4.y - q4.y);
+            u4.z = u4.z - dt * (p4.z - q4.z); u4.w = u4.w - dt * (p4.w - q4.w);
+            st4(urow, u4);
+        } else {
+            const float pp[3] = {p4.x, p4.y, p4.z};
+            for (int k = 0; k < n && k < 3; ++k) urow[k] = urow[k] - dt * (pp[k] - qrow[c0 + k]);
+        }
+    }
+    {                    // v[:, 1:-1] -= dt * (p[:, 1:] - p[:, :-1])
+        float* vrow = V + (size_t)i * pv + c0;
+        if (full) {
+            float4 v4 = *reinterpret_cast<const float4*>(vrow);
+            if (c0 > 0) v4.x = v4.x - dt * (p4.x - pl);
+            v4.y = v4.y - dt * (p4.y - p4.x); v4.z = v4.z - dt * (p4.z - p4.y); v4.w = v4.w - dt * (p4.w - p4.z);
+            st4(vrow, v4);
+        } else {
+            const float pp[4] = {pl, p4.x, p4.y, p4.z};
+            for (int k = 0; k < n && k < 3; ++k)
+                if (c0 + k > 0) vrow[k] = vrow[k] - dt * (pp[k + 1] - pp[k]);
+        }
     }
 }
 
 int launch_project(const smk_grid_t* g, const float* p, float* u, float* v, float dt, cudaStream_t s)
 {
-    dim3 grid((g->w + 31) / 32, (g->h + 7) / 8, g->batch), blk(32, 8);
+    dim3 grid((g->w + 127) / 128, (g->h + 7) / 8, g->batch), blk(32, 8);
     ProfScope prof_(SMK_PH_PROJECT, s);
     k_project<<<grid, blk, 0, s>>>(p, u, v, g->h, g->w, g->pitch_u, g->pitch_v, g->pitch_c,
                                    g->stride_u, g->stride_v, g->stride_c, dt);
@@ -206,30 +299,90 @@ int launch_bilerp(const float* f, int rows, int cols, int pitch, const float* y,
 }
 
 // ---- a10 (+a9, a11 epilogue): advection_step of one field by (u, v) ---------------------------------------
+// One thread per four consecutive cells of a row.  The velocity samples at the cell (a9: the closed form of
+// interpolate_velocity_u/v on the integer grid) come from three LDG.128; the back-traced bilinear gather (a8)
+// is four scalar loads per cell through the read-only path (for dt*|velocity| of a few cells they hit L1).
+// px, py are clamped to the field before the floor, so the lower corner needs no clamp and the upper corner a
+// single min; the corner coordinates stay in fp32 (exact below 2^24), which removes every int->float convert.
+struct AdvectArgs {
+    const float* F; float* O; int rows, cols, pitch; long long stride;
+    const float* U; const float* V; int h, w, pu, pv; long long su_, sv_;
+    float dt; int has_scale; float scale;
+    float* frame; long long frame_stride; int frame_pitch; const float* fmul;
+    unsigned ngroups; unsigned long long magic;          // row = (idx * magic) >> 40 == idx / ngroups (+ fix-up)
+};
+
 __global__ void __launch_bounds__(256)
-k_advect(const float* __restrict__ F, float* __restrict__ O, const int rows, const int cols, const int pitch,
-         const long long stride, const float* __restrict__ U, const float* __restrict__ V,
-         const int h, const int w, const int pu, const int pv, const long long su_, const long long sv_,
-         const float dt, const int has_scale, const float scale,
-         float* __restrict__ frame, const long long frame_stride, const int frame_pitch, const float* __restrict__ fmul)
+k_advect(const AdvectArgs a)
 {
-    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
-    if (i >= rows || j >= cols) return;
-    const size_t b = blockIdx.z;
-    const GlobalField f{F + b * stride, pitch}, fu{U + b * su_, pu}, fv{V + b * sv_, pv};
-    const float ui = interp_u_at(fu, h, w, i, j);                        // navier_stokes.py:84
-    const float vi = interp_v_at(fv, h, w, i, j);                        // navier_stokes.py:85
-    float px = (float)j - dt * ui;                                       // :87
-    float py = (float)i - dt * vi;                                       // :88
-    px = clampf(px, 0.0f, (float)(cols - 1));                            // :91
-    py = clampf(py, 0.0f, (float)(rows - 1));                            // :92
-    float val = bilerp(f, rows, cols, py, px);                           // :95
-    if (has_scale) val = val * scale;                                    // :171
-    O[b * stride + (size_t)i * pitch + j] = val;
-    if (frame) {                                                         // :173 (+ fractal_generator.py:62)
-        float fr = val;
-        if (fmul) fr = val + fmul[(size_t)i * frame_pitch + j] * val;
-        frame[b * frame_stride + (size_t)i * frame_pitch + j] = fr;
+    const unsigned idx = blockIdx.x * 256u + threadIdx.x;
+    unsigned row = (unsigned)(((unsigned long long)idx * a.magic) >> 40);
+    if (row * a.ngroups > idx) --row;
+    const int i = (int)row, c0 = (int)(idx - row * a.ngroups) * 4;
+    if (i >= a.rows) return;
+    const size_t b = blockIdx.y;
+    const float* __restrict__ F = a.F + b * a.stride;
+    const float* __restrict__ U = a.U + b * a.su_;
+    const float* __restrict__ V = a.V + b * a.sv_;
+    const int h = a.h, w = a.w, rows = a.rows, cols = a.cols, pitch = a.pitch;
+
+    // a9: u_i = 0.5*U[i][j] + 0.5*U[i][j+1] for j <= w-2 and i <= h-1, else 0      navier_stokes.py:97-102
+    float ui[4] = {0.f, 0.f, 0.f, 0.f}, vi[4] = {0.f, 0.f, 0.f, 0.f};
+    if (i <= h - 1 && c0 <= w - 2) {
+        const float* urow = U + (size_t)i * a.pu + c0;
+        float uu[5];
+        if (c0 + 4 < w) {
+            const float4 t = ld4(urow);
+            uu[0] = t.x; uu[1] = t.y; uu[2] = t.z; uu[3] = t.w; uu[4] = __ldg(urow + 4);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) uu[k] = (c0 + k < w) ? __ldg(urow + k) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c0 + k <= w - 2) ui[k] = 0.5f * uu[k] + 0.5f * uu[k + 1];
+    }
+    //     v_i = 0.5*V[i][j] + 0.5*V[i+1][j] for i <= h-2 and j <= w-1, else 0      navier_stokes.py:104-109
+    if (i <= h - 2 && c0 <= w - 1) {
+        const float* vrow = V + (size_t)i * a.pv + c0;               // pitch_v >= w+1 rounded up to 4: in bounds
+        const float4 t0 = ld4(vrow), t1 = ld4(vrow + a.pv);
+        vi[0] = 0.5f * t0.x + 0.5f * t1.x;
+        if (c0 + 1 <= w - 1) vi[1] = 0.5f * t0.y + 0.5f * t1.y;
+        if (c0 + 2 <= w - 1) vi[2] = 0.5f * t0.z + 0.5f * t1.z;
+        if (c0 + 3 <= w - 1) vi[3] = 0.5f * t0.w + 0.5f * t1.w;
+    }
+    const float xmax = (float)(cols - 1), ymax = (float)(rows - 1);
+    const float fi = (float)i;
+    float val[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float px = (float)(c0 + k) - a.dt * ui[k];                          // :87
+        float py = fi - a.dt * vi[k];                                       // :88
+        px = fminf(fmaxf(px, 0.0f), xmax);                                  // :91
+        py = fminf(fmaxf(py, 0.0f), ymax);                                  // :92
+        // a8 (:111-131) with x0 = floor(px) already inside [0, cols-1]
+        const float fx0 = floorf(px), fy0 = floorf(py);
+        const float fx1 = fminf(fx0 + 1.0f, xmax), fy1 = fminf(fy0 + 1.0f, ymax);
+        const int x0 = (int)fx0, y0 = (int)fy0;
+        const int dx = (fx1 != fx0) ? 1 : 0, dy = (fy1 != fy0) ? pitch : 0;
+        const float ax = fx1 - px, bx = px - fx0, ay = fy1 - py, by = py - fy0;
+        const float* q = F + (y0 * pitch + x0);
+        const float f00 = __ldg(q), f01 = __ldg(q + dx), f10 = __ldg(q + dy), f11 = __ldg(q + dy + dx);
+        float s = (ax * ay) * f00 + (bx * ay) * f01;
+        s = s + (ax * by) * f10;
+        s = s + (bx * by) * f11;
+        if (a.has_scale) s = s * a.scale;                                   // :171
+        val[k] = (c0 + k < cols) ? s : 0.0f;
+    }
+    // pitch is a multiple of 4, so the whole group lies inside the (padded) row: one STG.128, zeros in the padding
+    st4(a.O + b * a.stride + (size_t)i * pitch + c0, make_float4(val[0], val[1], val[2], val[3]));
+    if (a.frame) {                                                          // :173 (+ fractal_generator.py:62)
+        float4 fr = make_float4(val[0], val[1], val[2], val[3]);
+        if (a.fmul) {
+            const float4 m = ld4(a.fmul + (size_t)i * a.frame_pitch + c0);
+            fr.x = fr.x + m.x * fr.x; fr.y = fr.y + m.y * fr.y; fr.z = fr.z + m.z * fr.z; fr.w = fr.w + m.w * fr.w;
+        }
+        st4(a.frame + b * a.frame_stride + (size_t)i * a.frame_pitch + c0, fr);
     }
 }
 
@@ -237,11 +390,18 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
                   const float* u, const float* v, float dt, float scale, float* frame, int64_t frame_stride,
                   const float* fmul, cudaStream_t s)
 {
-    dim3 grid((cols + 31) / 32, (rows + 7) / 8, g->batch), blk(32, 8);
+    if ((int64_t)rows * pitch >= (1ll << 31)) return fail(SMK_EUNSUPPORTED, "smk_advect: field of %d x %d exceeds 2^31 elements", rows, pitch);
+    AdvectArgs a;
+    a.F = field; a.O = out; a.rows = rows; a.cols = cols; a.pitch = pitch; a.stride = stride;
+    a.U = u; a.V = v; a.h = g->h; a.w = g->w; a.pu = g->pitch_u; a.pv = g->pitch_v; a.su_ = g->stride_u; a.sv_ = g->stride_v;
+    a.dt = dt; a.has_scale = scale != 1.0f ? 1 : 0; a.scale = scale;
+    a.frame = frame; a.frame_stride = frame_stride; a.frame_pitch = g->pitch_c; a.fmul = fmul;
+    a.ngroups = (unsigned)((cols + 3) / 4);
+    a.magic = ((1ull << 40) + a.ngroups - 1) / a.ngroups;
+    const unsigned long long nthreads = (unsigned long long)rows * a.ngroups;
+    dim3 grid((unsigned)((nthreads + 255) / 256), g->batch);
     ProfScope prof_(rows == g->h + 1 ? SMK_PH_ADVECT_U : (cols == g->w + 1 ? SMK_PH_ADVECT_V : SMK_PH_ADVECT_D), s);
-    k_advect<<<grid, blk, 0, s>>>(field, out, rows, cols, pitch, stride, u, v, g->h, g->w, g->pitch_u, g->pitch_v,
-                                  g->stride_u, g->stride_v, dt, scale != 1.0f ? 1 : 0, scale,
-                                  frame, frame_stride, g->pitch_c, fmul);
+    k_advect<<<grid, 256, 0, s>>>(a);
     return check_launch("k_advect");
 }
 

@@ -315,6 +315,17 @@ class NavierStokesSimulator(nn.Module):
                   self._layout.h * self._layout.pitch_c, fmul.data_ptr() if fmul is not None else None, self._stream())
         return self._finish_frames(fr)
 
+    def step_into(self, frame, fmul=None):
+        """One time step whose returned copy is written into `frame`, a contiguous fp32 [batch, h, pitch_c]
+        device tensor owned by the caller (no allocation, no sync)."""
+        L = self._layout
+        if (tuple(frame.shape) != (L.batch, L.h, L.pitch_c) or not frame.is_contiguous()
+                or frame.dtype != torch.float32 or frame.device != self._cuda):
+            raise ValueError("frame must be a contiguous fp32 [%d, %d, %d] tensor on %s" % (L.batch, L.h, L.pitch_c, self._cuda))
+        prm = self._params()
+        _lib.call("smk_step", C.byref(self._grid), C.byref(self._state), C.byref(prm), frame.data_ptr(),
+                  L.h * L.pitch_c, fmul.data_ptr() if fmul is not None else None, self._stream())
+
     def run_steps(self, nsteps, fmul=None, return_frames=True, out=None):
         """nsteps consecutive steps enqueued back to back; returns frames [batch, nsteps, h, w] ([nsteps, h, w] if batch == 1).
 

@@ -44,27 +44,46 @@ class SmokeSimulator(nn.Module):
         return density
 
     # -------------------------------------------------------------- batched generation (data_loader.py:37-99)
-    def generate_sequences(self, emitters, sequence_length=20, add_fractal=True, host_out=None):
+    def generate_sequences(self, emitters, sequence_length=20, add_fractal=True, to_host=False):
         """Reset, splat one emitter list per simulation, run sequence_length steps.
 
         emitters[b] = [((x, y), intensity), ...] for simulation b (len == batch).  Returns frames
         [batch, sequence_length, h, w] -- each [b] is what the reference's per-sample loop stacks into
         sample['sequence'] (data_loader.py:66-68, :91).  History/chaos features are not touched.
-        host_out: optional pinned CPU tensor [batch, sequence_length, h, w]; the frames are copied into it
-        (device->host) and it is returned instead of the device tensor."""
+
+        to_host=True hands the frames back in pinned host memory (the dataset is pickled from the host,
+        data_loader.py:33-34): the frames of step t are copied device->host on a second stream while step
+        t+1 computes, from a time-major [sequence_length, batch, h, w] device buffer so every copy is one
+        contiguous block.  The returned tensor is the [batch, sequence_length, h, w] view of the pinned
+        time-major buffer, which this simulator owns and reuses on the next call."""
         ns = self.ns_solver
+        L = ns._layout
+        B, T = ns.batch, int(sequence_length)
         ns.setup_grid()
-        src, off, _ = ns.upload_sources([[(x, y, 8, inten) for (x, y), inten in lst] for lst in emitters],
-                                        pin=host_out is not None)
+        src, off, _ = ns.upload_sources([[(x, y, 8, inten) for (x, y), inten in lst] for lst in emitters], pin=to_host)
         ns.splat_uploaded(src, off)
         fmul = self.fractal_gen.multiplier((ns.h, ns.w), 0.05) if add_fractal else None
-        fr = ns.run_steps(sequence_length, fmul=fmul)
-        fr = fr if ns.batch > 1 else fr.unsqueeze(0)
-        if host_out is not None:
-            host_out.copy_(fr, non_blocking=True)
-            torch.cuda.current_stream(ns._cuda).synchronize()
-            return host_out
-        return fr
+        if not to_host:
+            fr = ns.run_steps(T, fmul=fmul)
+            return fr if B > 1 else fr.unsqueeze(0)
+        key = (T,)
+        if getattr(self, "_gen_key", None) != key:
+            self._gen_dev = torch.empty(T, B, L.h, L.pitch_c, dtype=torch.float32, device=ns._cuda)
+            self._gen_host = torch.empty(T, B, L.h, L.pitch_c, dtype=torch.float32).pin_memory()
+            self._gen_copy_stream = torch.cuda.Stream(device=ns._cuda)
+            self._gen_key = key
+        dev, host, cs = self._gen_dev, self._gen_host, self._gen_copy_stream
+        main = torch.cuda.current_stream(ns._cuda)
+        cs.wait_stream(main)                      # the previous call's consumer is done with the buffers
+        for t in range(T):
+            ns.step_into(dev[t], fmul=fmul)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            cs.wait_event(ev)
+            with torch.cuda.stream(cs):
+                host[t].copy_(dev[t], non_blocking=True)
+        cs.synchronize()
+        return host.permute(1, 0, 2, 3)[..., :L.w]
 
     # -------------------------------------------------------------- chaos features (smoke_simulator.py:47-140)
     def get_chaos_features(self):

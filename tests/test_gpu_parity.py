@@ -339,6 +339,10 @@ def test_generate_sequences_matches_loop():
     ems = [[((x, y), i) for x, y, _, i in emitters_for_sequence(s)] for s in range(B)]
     bat = SmokeSimulator((128, 128), device="cuda", batch=B)
     fr = N(bat.generate_sequences(ems, L))
+    for _ in range(2):                                   # the pinned, double-streamed path reuses its buffers
+        fr_h = bat.generate_sequences(ems, L, to_host=True)
+        assert fr_h.device.type == "cpu" and fr_h.is_pinned() and tuple(fr_h.shape) == (B, L, 128, 128)
+        assert_same(fr_h.numpy(), fr, "to_host frames")
     one = SmokeSimulator((128, 128), device="cuda")
     for s in range(B):
         one.ns_solver.setup_grid()
