@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMK_ABI_VERSION 1
+#define SMK_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SMK_API __attribute__((visibility("default")))
@@ -51,7 +51,19 @@ typedef struct smk_grid {
     int64_t stride_u;    /* elements between consecutive simulations' u                           */
     int64_t stride_v;
     int64_t stride_c;
+    /* Row-slab decomposition (large single grids split over GPUs).  The arrays hold h local cell rows
+     * (ghost rows included) that start at global cell row row0 of a gh-row grid.  gh == 0 means "not a
+     * slab" (row0 = 0, gh = h).  Only the advection (absolute fp32 coordinates, global edge tests) and the
+     * emitter splat look at these; every other phase is a purely local stencil. */
+    int32_t row0, gh;
 } smk_grid_t;
+
+/* Slab advection guard: cells in local rows [need_lo, need_hi) must gather only from local rows
+ * [valid_lo, valid_hi) of the advected field; otherwise *overflow_flag (device int32) is set to 1. */
+typedef struct smk_slab_check {
+    int32_t need_lo, need_hi, valid_lo, valid_hi;
+    int32_t* overflow_flag;
+} smk_slab_check_t;
 
 /* One Gaussian emitter, add_smoke_source(x, y, radius, intensity): navier_stokes.py:37 */
 typedef struct smk_source {
@@ -139,9 +151,15 @@ SMK_API int smk_bilerp(const float* field, int32_t rows, int32_t cols, int32_t p
 SMK_API int smk_advect(const smk_grid_t* g, const float* field, float* out, int32_t rows, int32_t cols,
                int32_t pitch, int64_t stride, const float* u, const float* v, float dt,
                float scale, float* frame, int64_t frame_stride, const float* fmul, void* stream);
+/*     the same on a row slab (g->gh != 0): coordinates and edge tests are global, memory is local;
+ *     chk (may be NULL) guards the gather reach. */
+SMK_API int smk_advect_slab(const smk_grid_t* g, const float* field, float* out, int32_t rows, int32_t cols,
+                    int32_t pitch, const float* u, const float* v, float dt, float scale,
+                    const smk_slab_check_t* chk, void* stream);
 
 /* a3-a11 one full step() / n steps (navier_stokes.py:151-173) over the state.  frames (may be NULL):
- *     [batch][nsteps][h][pitch_c] returned copies, multiplied by (1+fmul) when fmul != NULL. */
+ *     [batch][nsteps][h][pitch_c] returned copies, multiplied by (1+fmul) when fmul != NULL.
+ *     Not available on a slab grid (the host interleaves halo exchanges between the phases). */
 SMK_API int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
              float* frame, int64_t frame_stride, const float* fmul, void* stream);
 SMK_API int smk_run_steps(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, int32_t nsteps,

@@ -36,6 +36,7 @@ def lib():
             "smk_oracle_interp_u": [f32p, i, i, i, i, f32p],
             "smk_oracle_interp_v": [f32p, i, i, i, i, f32p],
             "smk_oracle_advect": [f32p, f32p, i, i, f32p, f32p, i, i, f],
+            "smk_oracle_advect_slab": [f32p, f32p, i, i, f32p, f32p, i, i, f, i, i],
             "smk_oracle_diffuse": [f32p, f32p, i, i, f],
             "smk_oracle_buoyancy": [f32p, f32p, i, i, f],
             "smk_oracle_divergence": [f32p, f32p, f32p, i, i, f],
@@ -92,6 +93,30 @@ def advection_step(field, u, v, dt):
     out = np.empty_like(field)
     lib().smk_oracle_advect(field, out, field.shape[0], field.shape[1], u, v, h, w, np.float32(dt))
     return out
+
+
+def advection_step_slab(field, u, v, dt, row0, gh):
+    """Extension (no reference counterpart): advection of a row slab whose local row 0 is global row row0 of a
+    gh-row grid; equals advection_step of the whole grid on the rows the slab holds exactly."""
+    field, u, v = _c(field), _c(u), _c(v)
+    h, w = v.shape[0], u.shape[1]
+    out = np.empty_like(field)
+    lib().smk_oracle_advect_slab(field, out, field.shape[0], field.shape[1], u, v, h, w, np.float32(dt), int(row0), int(gh))
+    return out
+
+
+def buoyancy(v, d, dt):
+    """navier_stokes.py:154-155 (returns the new v)"""
+    v, d = _c(v).copy(), _c(d)
+    lib().smk_oracle_buoyancy(v, d, d.shape[0], d.shape[1], np.float32(dt))
+    return v
+
+
+def grad_subtract(u, v, p, dt):
+    """navier_stokes.py:148-149 (returns new u, v)"""
+    u, v, p = _c(u).copy(), _c(v).copy(), _c(p)
+    lib().smk_oracle_grad_subtract(u, v, p, p.shape[0], p.shape[1], np.float32(dt))
+    return u, v
 
 
 def interpolate_velocity(u, v, rows, cols):

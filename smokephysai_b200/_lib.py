@@ -14,7 +14,13 @@ c_f, c_i32, c_i64, c_p = C.c_float, C.c_int32, C.c_int64, C.c_void_p
 class Grid(C.Structure):                     # smk_grid_t
     _fields_ = [("h", c_i32), ("w", c_i32), ("batch", c_i32),
                 ("pitch_u", c_i32), ("pitch_v", c_i32), ("pitch_c", c_i32),
-                ("stride_u", c_i64), ("stride_v", c_i64), ("stride_c", c_i64)]
+                ("stride_u", c_i64), ("stride_v", c_i64), ("stride_c", c_i64),
+                ("row0", c_i32), ("gh", c_i32)]
+
+
+class SlabCheck(C.Structure):                # smk_slab_check_t
+    _fields_ = [("need_lo", c_i32), ("need_hi", c_i32), ("valid_lo", c_i32), ("valid_hi", c_i32),
+                ("overflow_flag", c_p)]
 
 
 class Source(C.Structure):                   # smk_source_t
@@ -50,6 +56,7 @@ SIGNATURES = {
     "smk_project": [GP, c_p, c_p, c_p, c_f, c_p],
     "smk_bilerp": [c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i64, c_i32, c_p],
     "smk_advect": [GP, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_f, c_f, c_p, c_i64, c_p, c_p],
+    "smk_advect_slab": [GP, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_f, c_f, C.POINTER(SlabCheck), c_p],
     "smk_step": [GP, SP, PP, c_p, c_i64, c_p, c_p],
     "smk_run_steps": [GP, SP, PP, c_i32, c_p, c_i64, c_i64, c_p, c_p],
     "smk_div_norms": [GP, c_p, c_p, c_p, c_p],

@@ -65,6 +65,9 @@ int check_grid(const smk_grid_t* g, const char* who)
     if (g->batch > 1 && (g->stride_u < (int64_t)(g->h + 1) * g->pitch_u || g->stride_v < (int64_t)g->h * g->pitch_v ||
                          g->stride_c < (int64_t)g->h * g->pitch_c))
         return fail(SMK_EINVAL, "%s: batch stride smaller than one field", who);
+    if (g->gh != 0 && (g->row0 < 0 || g->row0 + g->h > g->gh))
+        return fail(SMK_EINVAL, "%s: slab rows [%d, %d) outside the global grid of %d rows", who, g->row0, g->row0 + g->h, g->gh);
+    if (g->gh == 0 && g->row0 != 0) return fail(SMK_EINVAL, "%s: row0 set without gh", who);
     return SMK_OK;
 }
 
@@ -227,13 +230,29 @@ int smk_advect(const smk_grid_t* g, const float* field, float* out, int32_t rows
     if (out == u || out == v) return fail(SMK_EINVAL, "smk_advect: out aliases a velocity input");
     if (rows < 1 || cols < 1 || pitch < cols) return fail(SMK_EINVAL, "smk_advect: bad field shape %d x %d pitch %d", rows, cols, pitch);
     if (frame && (rows != g->h || cols != g->w)) return fail(SMK_EINVAL, "smk_advect: frame output needs a cell-centred field");
-    return launch_advect(g, field, out, rows, cols, pitch, stride, u, v, dt, scale, frame, frame_stride, fmul, (cudaStream_t)stream);
+    return launch_advect(g, field, out, rows, cols, pitch, stride, u, v, dt, scale, frame, frame_stride, fmul, nullptr, (cudaStream_t)stream);
+}
+
+int smk_advect_slab(const smk_grid_t* g, const float* field, float* out, int32_t rows, int32_t cols, int32_t pitch,
+                    const float* u, const float* v, float dt, float scale, const smk_slab_check_t* chk, void* stream)
+{
+    SMK_TRY(check_grid(g, "smk_advect_slab"));
+    if (g->gh == 0) return fail(SMK_EINVAL, "smk_advect_slab: the grid is not a slab (gh == 0)");
+    if (g->batch != 1) return fail(SMK_EUNSUPPORTED, "smk_advect_slab: batch must be 1");
+    if (!field || !out || !u || !v) return fail(SMK_EINVAL, "smk_advect_slab: NULL pointer");
+    if (field == out || out == u || out == v) return fail(SMK_EINVAL, "smk_advect_slab: out aliases an input");
+    if (rows < 1 || cols < 1 || pitch < cols) return fail(SMK_EINVAL, "smk_advect_slab: bad field shape %d x %d pitch %d", rows, cols, pitch);
+    if (chk && (!chk->overflow_flag || chk->need_lo > chk->need_hi || chk->valid_lo > chk->valid_hi))
+        return fail(SMK_EINVAL, "smk_advect_slab: bad check ranges");
+    return launch_advect(g, field, out, rows, cols, pitch, 0, u, v, dt, scale, nullptr, 0, nullptr, chk, (cudaStream_t)stream);
 }
 
 int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, float* frame, int64_t frame_stride,
              const float* fmul, void* stream)
 {
     SMK_TRY(check_grid(g, "smk_step"));
+    if (g->gh != 0 && (g->gh != g->h || g->row0 != 0))
+        return fail(SMK_EUNSUPPORTED, "smk_step: slab grids are stepped phase by phase with halo exchanges in between");
     if (!st || !prm) return fail(SMK_EINVAL, "smk_step: state/params NULL");
     SMK_TRY(check_ptrs("smk_step", {st->u[0], st->u[1], st->v[0], st->v[1], st->d[0], st->d[1], st->p[0], st->p[1], st->div}));
     if ((st->cur_u | st->cur_v | st->cur_d | st->cur_p) & ~1) return fail(SMK_EINVAL, "smk_step: cur_* must be 0 or 1");
@@ -250,9 +269,9 @@ int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, floa
     st->cur_p ^= flip;
     SMK_TRY(launch_project(g, st->p[st->cur_p], u1, v1, prm->dt, s));
     // 4. sequential advection: u, then v with the new u, then density with both :166-168; 5. decay :171; copy :173
-    SMK_TRY(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, g->stride_u, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, s));
-    SMK_TRY(launch_advect(g, v1, v0, g->h, g->w + 1, g->pitch_v, g->stride_v, u0, v1, prm->dt, 1.0f, nullptr, 0, nullptr, s));
-    SMK_TRY(launch_advect(g, d1, d0, g->h, g->w, g->pitch_c, g->stride_c, u0, v0, prm->dt, prm->decay, frame, frame_stride, fmul, s));
+    SMK_TRY(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, g->stride_u, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, nullptr, s));
+    SMK_TRY(launch_advect(g, v1, v0, g->h, g->w + 1, g->pitch_v, g->stride_v, u0, v1, prm->dt, 1.0f, nullptr, 0, nullptr, nullptr, s));
+    SMK_TRY(launch_advect(g, d1, d0, g->h, g->w, g->pitch_c, g->stride_c, u0, v0, prm->dt, prm->decay, frame, frame_stride, fmul, nullptr, s));
     return SMK_OK;
 }
 

@@ -17,6 +17,7 @@
 // per-cell multiplier (0.25 inside, 0 on the ring/outside), which costs no extra instruction.
 //
 // Bit-exactness: the association above is kept literally; 0.25*x == x*0.25 in IEEE; no FMA (-fmad=false).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace smk {
@@ -116,15 +117,43 @@ static int ntiles(int n, int tile, int halo)
     return (n - tile + adv - 1) / adv + 1;
 }
 
+// Sweeps per launch for an overlapped-tile run, from a cost model fitted on a B200 (tools/tune_jacobi.py):
+//   time = launches * 2.3 us  +  sum over launches of  waves * (3 us + T * 0.56 us)        (128 x 128 tiles, 1 CTA / SM)
+// Small grids want the largest T that still fits one wave of CTAs; large grids settle near T = 12, where the
+// halo redundancy ((128 / (128 - 2 HX)) * (128 / (128 - 2 T))) starts to outweigh the saved loads.
+static int pick_T(const smk_grid_t* g, int K, int TH, int tmax, int sms)
+{
+    double best = 1e30; int bestT = 1;
+    for (int nl = 1; nl <= K; ++nl) {
+        const int T = (K + nl - 1) / nl;
+        if (T > tmax) continue;
+        double cost = 2.3 * nl;
+        int left = K;
+        for (int l = 0; l < nl; ++l) {
+            const int t = (left + (nl - l) - 1) / (nl - l);       // balanced split
+            left -= t;
+            const int HX = (t + 3) & ~3;
+            const long ctas = (long)ntiles(g->w, 128, HX) * ntiles(g->h, TH, t) * g->batch;
+            const long waves = (ctas + sms - 1) / sms;
+            cost += waves * (3.0 + 0.56 * t);
+        }
+        if (cost < best) { best = cost; bestT = T; }
+        if (T == 1) break;
+    }
+    return bestT;
+}
+
 template <int R, int NW>
 static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, int K, int T, int* in_scratch, cudaStream_t s)
 {
     const int TH = R * NW;
     const bool whole = (g->h <= TH) && (g->w <= 128);
     float* src = a; float* dst = b;
-    int done = 0;
-    while (done < K) {
-        int t = whole ? (K - done) : min(T, K - done);
+    int left = K;
+    int nl = whole ? 1 : (K + T - 1) / T;
+    for (int l = 0; l < nl; ++l) {
+        const int t = (left + (nl - l) - 1) / (nl - l);           // K sweeps split evenly over the launches
+        left -= t;
         const int HX = (t + 3) & ~3;
         const int nx = ntiles(g->w, 128, HX), ny = ntiles(g->h, TH, t);
         dim3 grid(nx, ny, g->batch);
@@ -137,10 +166,19 @@ static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, in
         }
         if (rc != SMK_OK) return rc;
         float* tmp = src; src = dst; dst = tmp;
-        done += t;
     }
     *in_scratch = (src == b) ? 1 : 0;
     return SMK_OK;
+}
+
+static int sm_count()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
 }
 
 int launch_jacobi(const smk_grid_t* g, const float* div, float* p, float* scratch, int K, int T, int* in_scratch, cudaStream_t s)
@@ -148,13 +186,16 @@ int launch_jacobi(const smk_grid_t* g, const float* div, float* p, float* scratc
     *in_scratch = 0;
     if (K <= 0) return SMK_OK;
     if (g->batch > 65535) return fail(SMK_EUNSUPPORTED, "smk_jacobi: batch %d > 65535", g->batch);
-    if (T <= 0) T = 8;
-    if (g->w <= 128 && g->h <= 32) return run_cfg<4, 8>(g, div, p, scratch, K, T, in_scratch, s);
-    if (g->w <= 128 && g->h <= 64) return run_cfg<8, 8>(g, div, p, scratch, K, T, in_scratch, s);
-    if (g->w <= 128 && g->h <= 128) return run_cfg<8, 16>(g, div, p, scratch, K, T, in_scratch, s);
+    if (g->w <= 128 && g->h <= 32) return run_cfg<4, 8>(g, div, p, scratch, K, T > 0 ? T : 8, in_scratch, s);
+    if (g->w <= 128 && g->h <= 64) return run_cfg<8, 8>(g, div, p, scratch, K, T > 0 ? T : 8, in_scratch, s);
+    if (g->w <= 128 && g->h <= 128) return run_cfg<8, 16>(g, div, p, scratch, K, T > 0 ? T : 8, in_scratch, s);
     // large grids: overlapped tiles.  T must leave a positive advance in both directions.
-    if (T > 24) T = 24;
-    return run_cfg<8, 16>(g, div, p, scratch, K, T, in_scratch, s);
+    int tile = 0;                                   // 0 auto, 1: 64 x 128 (8 warps), 2: 128 x 128 (16 warps), 3: 64 x 128 (16 warps)
+    if (const char* e = getenv("SMK_JACOBI_TILE")) tile = atoi(e);
+    if (T <= 0) T = (tile == 1 || tile == 3) ? 8 : pick_T(g, K, 128, 24, sm_count());
+    if (tile == 1) return run_cfg<8, 8>(g, div, p, scratch, K, min(T, 12), in_scratch, s);
+    if (tile == 3) return run_cfg<4, 16>(g, div, p, scratch, K, min(T, 12), in_scratch, s);
+    return run_cfg<8, 16>(g, div, p, scratch, K, min(T, 24), in_scratch, s);
 }
 
 }  // namespace smk

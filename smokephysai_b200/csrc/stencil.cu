@@ -310,8 +310,11 @@ struct AdvectArgs {
     float dt; int has_scale; float scale;
     float* frame; long long frame_stride; int frame_pitch; const float* fmul;
     unsigned ngroups; unsigned long long magic;          // row = (idx * magic) >> 40 == idx / ngroups (+ fix-up)
+    int row0, gh;                                        // slab: global row of local row 0, global cell rows
+    int need_lo, need_hi, valid_lo, valid_hi; int* overflow;
 };
 
+template <bool SLAB>
 __global__ void __launch_bounds__(256)
 k_advect(const AdvectArgs a)
 {
@@ -324,11 +327,15 @@ k_advect(const AdvectArgs a)
     const float* __restrict__ F = a.F + b * a.stride;
     const float* __restrict__ U = a.U + b * a.su_;
     const float* __restrict__ V = a.V + b * a.sv_;
-    const int h = a.h, w = a.w, rows = a.rows, cols = a.cols, pitch = a.pitch;
+    const int w = a.w, rows = a.rows, cols = a.cols, pitch = a.pitch;
+    // slab: h is the GLOBAL cell-row count and gi the global row of this thread's cells; memory stays local
+    const int h = SLAB ? a.gh : a.h;
+    const int gi = SLAB ? i + a.row0 : i;
+    const int grows = SLAB ? rows - a.h + a.gh : rows;
 
     // a9: u_i = 0.5*U[i][j] + 0.5*U[i][j+1] for j <= w-2 and i <= h-1, else 0      navier_stokes.py:97-102
     float ui[4] = {0.f, 0.f, 0.f, 0.f}, vi[4] = {0.f, 0.f, 0.f, 0.f};
-    if (i <= h - 1 && c0 <= w - 2) {
+    if (gi <= h - 1 && c0 <= w - 2) {
         const float* urow = U + (size_t)i * a.pu + c0;
         float uu[5];
         if (c0 + 4 < w) {
@@ -343,7 +350,7 @@ k_advect(const AdvectArgs a)
             if (c0 + k <= w - 2) ui[k] = 0.5f * uu[k] + 0.5f * uu[k + 1];
     }
     //     v_i = 0.5*V[i][j] + 0.5*V[i+1][j] for i <= h-2 and j <= w-1, else 0      navier_stokes.py:104-109
-    if (i <= h - 2 && c0 <= w - 1) {
+    if (gi <= h - 2 && c0 <= w - 1 && (!SLAB || i + 1 < a.h)) {
         const float* vrow = V + (size_t)i * a.pv + c0;               // pitch_v >= w+1 rounded up to 4: in bounds
         const float4 t0 = ld4(vrow), t1 = ld4(vrow + a.pv);
         vi[0] = 0.5f * t0.x + 0.5f * t1.x;
@@ -351,8 +358,8 @@ k_advect(const AdvectArgs a)
         if (c0 + 2 <= w - 1) vi[2] = 0.5f * t0.z + 0.5f * t1.z;
         if (c0 + 3 <= w - 1) vi[3] = 0.5f * t0.w + 0.5f * t1.w;
     }
-    const float xmax = (float)(cols - 1), ymax = (float)(rows - 1);
-    const float fi = (float)i;
+    const float xmax = (float)(cols - 1), ymax = (float)(grows - 1);
+    const float fi = (float)gi;
     float val[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -363,8 +370,17 @@ k_advect(const AdvectArgs a)
         // a8 (:111-131) with x0 = floor(px) already inside [0, cols-1]
         const float fx0 = floorf(px), fy0 = floorf(py);
         const float fx1 = fminf(fx0 + 1.0f, xmax), fy1 = fminf(fy0 + 1.0f, ymax);
-        const int x0 = (int)fx0, y0 = (int)fy0;
-        const int dx = (fx1 != fx0) ? 1 : 0, dy = (fy1 != fy0) ? pitch : 0;
+        const int x0 = (int)fx0;
+        int y0 = (int)fy0;
+        const int dx = (fx1 != fx0) ? 1 : 0;
+        int dy = (fy1 != fy0) ? pitch : 0;
+        if (SLAB) {                                                         // global -> local row, kept inside the slab
+            y0 -= a.row0;
+            const int y1 = y0 + (dy ? 1 : 0);
+            if (i >= a.need_lo && i < a.need_hi && (y0 < a.valid_lo || y1 >= a.valid_hi) && a.overflow) *a.overflow = 1;
+            if (y1 > rows - 1) dy = 0;
+            y0 = clampi(y0, 0, rows - 1);
+        }
         const float ax = fx1 - px, bx = px - fx0, ay = fy1 - py, by = py - fy0;
         const float* q = F + (y0 * pitch + x0);
         const float f00 = __ldg(q), f01 = __ldg(q + dx), f10 = __ldg(q + dy), f11 = __ldg(q + dy + dx);
@@ -388,7 +404,7 @@ k_advect(const AdvectArgs a)
 
 int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows, int cols, int pitch, int64_t stride,
                   const float* u, const float* v, float dt, float scale, float* frame, int64_t frame_stride,
-                  const float* fmul, cudaStream_t s)
+                  const float* fmul, const smk_slab_check_t* chk, cudaStream_t s)
 {
     if ((int64_t)rows * pitch >= (1ll << 31)) return fail(SMK_EUNSUPPORTED, "smk_advect: field of %d x %d exceeds 2^31 elements", rows, pitch);
     AdvectArgs a;
@@ -398,10 +414,15 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
     a.frame = frame; a.frame_stride = frame_stride; a.frame_pitch = g->pitch_c; a.fmul = fmul;
     a.ngroups = (unsigned)((cols + 3) / 4);
     a.magic = ((1ull << 40) + a.ngroups - 1) / a.ngroups;
+    const bool slab = g->gh != 0 && (g->gh != g->h || g->row0 != 0);
+    a.row0 = g->row0; a.gh = g->gh;
+    a.need_lo = chk ? chk->need_lo : 0; a.need_hi = chk ? chk->need_hi : 0;
+    a.valid_lo = chk ? chk->valid_lo : 0; a.valid_hi = chk ? chk->valid_hi : 0; a.overflow = chk ? chk->overflow_flag : nullptr;
     const unsigned long long nthreads = (unsigned long long)rows * a.ngroups;
     dim3 grid((unsigned)((nthreads + 255) / 256), g->batch);
     ProfScope prof_(rows == g->h + 1 ? SMK_PH_ADVECT_U : (cols == g->w + 1 ? SMK_PH_ADVECT_V : SMK_PH_ADVECT_D), s);
-    k_advect<<<grid, 256, 0, s>>>(a);
+    if (slab) k_advect<true><<<grid, 256, 0, s>>>(a);
+    else      k_advect<false><<<grid, 256, 0, s>>>(a);
     return check_launch("k_advect");
 }
 

@@ -34,8 +34,9 @@ class FieldLayout:
     """
     FIELDS = ("u0", "u1", "v0", "v1", "d0", "d1", "p0", "p1", "div", "boundary")
 
-    def __init__(self, h, w, batch=1):
+    def __init__(self, h, w, batch=1, row0=0, gh=0):
         self.h, self.w, self.batch = int(h), int(w), int(batch)
+        self.row0, self.gh = int(row0), int(gh)            # row-slab placement inside a gh-row grid (0 = not a slab)
         if self.h < 1 or self.w < 1 or self.batch < 1:
             raise ValueError("grid_size and batch must be positive, got %r x %r, batch %r" % (h, w, batch))
         self.pitch_u = _round4(self.w)
@@ -68,7 +69,7 @@ class FieldLayout:
 
     def grid_struct(self):
         return Grid(self.h, self.w, self.batch, self.pitch_u, self.pitch_v, self.pitch_c,
-                    self.stride_u, self.stride_v, self.stride_c)
+                    self.stride_u, self.stride_v, self.stride_c, self.row0, self.gh)
 
 
 def resolve_devices(device):
@@ -86,7 +87,7 @@ class NavierStokesSimulator(nn.Module):
     """Simplified Navier-Stokes smoke solver (reference: navier_stokes.py:6)."""
 
     def __init__(self, grid_size=(128, 128), dt=0.01, viscosity=0.001, device="cuda", *,
-                 jacobi_iters=20, batch=1, sweeps_per_launch=0):
+                 jacobi_iters=20, batch=1, sweeps_per_launch=0, _slab=None):
         super().__init__()
         self.grid_size = grid_size
         self.dt = dt
@@ -98,7 +99,8 @@ class NavierStokesSimulator(nn.Module):
         self.sweeps_per_launch = int(sweeps_per_launch)
         self._cuda, self._out_device = resolve_devices(device)
         self._lib = _lib.load()
-        self._layout = FieldLayout(self.h, self.w, self.batch)
+        row0, gh = _slab if _slab is not None else (0, 0)   # (global row of local row 0, global rows): slab.py
+        self._layout = FieldLayout(self.h, self.w, self.batch, row0, gh)
         self._grid = self._layout.grid_struct()
         self._arena = None
         self._state = State()

@@ -1,0 +1,321 @@
+"""Row-slab decomposition of one large grid over several GPUs (BASELINE config 4:
+"single 8192x8192 grid slab-decomposed across 2/4/8 B200 with per-sweep NCCL halo exchange over NVLink").
+
+The reference has nothing like this (single process, single device); it is an extension behind the same
+solver semantics, and its contract is: the slab run is BIT-IDENTICAL to the undecomposed run.
+
+How.  Rank r owns the cell rows [R0, R1) of the H x W grid and stores [A, B) = [R0 - halo, R1 + halo)
+clipped to the grid ("ghost rows").  Every phase of the step is a local stencil with fixed arithmetic, so
+evaluating it redundantly on the ghost rows gives exactly the values the neighbour computes; each phase
+only erodes the band of exact rows by its stencil radius.  A halo exchange (rows are contiguous in memory:
+one send and one receive of `rows x pitch` floats per neighbour and field) refreshes the ghosts:
+
+    exchange(u, v, density)                               once per step
+    forces + diffusion + divergence                       erodes 1 row (2 for div)
+    for each launch of t <= T fused Jacobi sweeps:        erodes t rows of p
+        exchange(p)                                       -- "every sweep" when T = 1; deep halos when T > 1
+    gradient subtract, advect u, v, density               erode 1 + (reach + 1) rows, reach = |dt * velocity|
+
+so halo >= T + 4 rows keeps every owned row exact as long as the back-trace reaches at most halo - 4 rows;
+the advect kernel checks that on the device (smk_slab_check_t) and `check()` raises if it was violated.
+Only the advection needs to know where the slab sits (absolute fp32 coordinates, global edge tests:
+smk_grid_t.row0 / gh); all other kernels run on the slab as if it were a small grid, because a slab edge
+that is not a grid edge only produces garbage in ghost rows that are already written off.
+
+Exchangers: `DistExchanger` (torch.distributed P2P: NCCL over NVLink on GPUs, gloo in the CPU tests) and
+`LocalGroup` (all slabs in one process on one GPU: the way to test the decomposition without a multi-GPU box).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import SlabCheck
+
+
+class SlabGeometry:
+    """Pure host arithmetic of the decomposition (testable without a GPU)."""
+
+    def __init__(self, H, W, world, rank, halo):
+        self.H, self.W, self.world, self.rank, self.halo = int(H), int(W), int(world), int(rank), int(halo)
+        if not (0 <= self.rank < self.world):
+            raise ValueError("rank %d outside world of %d" % (rank, world))
+        self.splits = self.split(self.H, self.world)
+        self.R0, self.R1 = self.splits[self.rank]
+        if self.world > 1 and min(b - a for a, b in self.splits) < self.halo + 1:
+            raise ValueError("slabs of %d rows are too thin for a halo of %d rows (need >= halo + 1)"
+                             % (min(b - a for a, b in self.splits), self.halo))
+        self.A, self.B = self.stored(self.rank)
+        self.hl = self.B - self.A                    # local cell rows (u has hl + 1)
+        self.top_edge, self.bottom_edge = self.A == 0, self.B == self.H
+        self.own_lo, self.own_hi = self.R0 - self.A, self.R1 - self.A      # owned rows, local indices
+
+    @staticmethod
+    def split(H, world):
+        base, rem = divmod(H, world)
+        out, r0 = [], 0
+        for r in range(world):
+            n = base + (1 if r < rem else 0)
+            out.append((r0, r0 + n))
+            r0 += n
+        return out
+
+    def stored(self, rank):
+        r0, r1 = self.splits[rank]
+        return max(0, r0 - self.halo), min(self.H, r1 + self.halo)
+
+    def rows(self, kind):
+        """Local rows of a field: 'u' is staggered along y (hl + 1 rows), everything else has hl."""
+        return self.hl + 1 if kind == "u" else self.hl
+
+    def blocks(self, kind):
+        """-> (sends, recvs), lists of (peer, first local row, number of rows) in a fixed order
+        (upper neighbour first), identical on both sides of every pair."""
+        sends, recvs = [], []
+        extra = 1 if kind == "u" else 0
+        r = self.rank
+        if r > 0:                                            # upper neighbour r-1
+            n = self.R0 - self.A
+            recvs.append((r - 1, 0, n))
+            b_up = self.stored(r - 1)[1]                     # it stores [.., b_up): its lower ghost is [R0, b_up) (+1 row of u)
+            sends.append((r - 1, self.R0 - self.A, b_up - self.R0 + extra))
+        if r < self.world - 1:                               # lower neighbour r+1
+            recvs.append((r + 1, self.R1 - self.A, self.B - self.R1 + extra))
+            a_dn = self.stored(r + 1)[0]                     # its upper ghost is [a_dn, R1)
+            sends.append((r + 1, a_dn - self.A, self.R1 - a_dn))
+        return sends, recvs
+
+    def owned_rows(self, kind):
+        """Local [lo, hi) of the rows this rank owns (the last rank also owns u's row H)."""
+        hi = self.own_hi + (1 if kind == "u" and self.rank == self.world - 1 else 0)
+        return self.own_lo, hi
+
+
+def sweep_split(K, T):
+    """K sweeps over ceil(K/T) launches, as evenly as possible (same rule as the library's tiled runs)."""
+    if K <= 0:
+        return []
+    nl = (K + T - 1) // T
+    out, left = [], K
+    for l in range(nl):
+        t = (left + (nl - l) - 1) // (nl - l)
+        out.append(t)
+        left -= t
+    return out
+
+
+class DistExchanger:
+    """Halo exchange over torch.distributed point-to-point ops (NCCL send/recv on GPUs, gloo on CPU)."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def exchange(self, geom, tensors):
+        """tensors: list of (contiguous [rows, pitch] tensor, kind)."""
+        import torch.distributed as dist
+        ops = []
+        for t, kind in tensors:
+            sends, recvs = geom.blocks(kind)
+            for peer, a, n in recvs:
+                ops.append(dist.P2POp(dist.irecv, t[a:a + n], peer, self.group))
+            for peer, a, n in sends:
+                ops.append(dist.P2POp(dist.isend, t[a:a + n], peer, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+
+def local_exchange(geoms, tensor_lists):
+    """In-process exchange between all slabs: tensor_lists[r] = list of (tensor, kind) of rank r."""
+    for r, geom in enumerate(geoms):
+        for k, (t, kind) in enumerate(tensor_lists[r]):
+            _, recvs = geom.blocks(kind)
+            for peer, a, n in recvs:
+                sends, _ = geoms[peer].blocks(kind)
+                b, m = next((b, m) for p, b, m in sends if p == r)
+                assert m == n, "halo plan mismatch between rank %d and %d" % (r, peer)
+                t[a:a + n].copy_(tensor_lists[peer][k][0][b:b + m])
+
+
+class SlabNavierStokes:
+    """One rank's slab of a NavierStokesSimulator (navier_stokes.py:6-173 semantics on the global grid)."""
+
+    def __init__(self, grid_size, dt=0.01, viscosity=0.001, device="cuda", *, rank, world, jacobi_iters=20,
+                 sweeps_per_launch=10, halo=None, exchanger=None):
+        from .navier_stokes import NavierStokesSimulator
+        H, W = int(grid_size[0]), int(grid_size[1])
+        self.T = max(1, int(sweeps_per_launch))
+        self.halo = int(halo) if halo is not None else self.T + 4
+        if world > 1 and self.halo < self.T + 3:
+            raise ValueError("halo of %d rows is too shallow for %d fused sweeps per launch (need >= T + 3)" % (self.halo, self.T))
+        self.geom = SlabGeometry(H, W, world, rank, self.halo if world > 1 else 0)
+        self.grid_size, self.dt, self.viscosity = (H, W), dt, viscosity
+        self.jacobi_iters = int(jacobi_iters)
+        self.rank, self.world = int(rank), int(world)
+        self.local = NavierStokesSimulator((self.geom.hl, W), dt, viscosity, device, jacobi_iters=jacobi_iters,
+                                           sweeps_per_launch=self.T, _slab=(self.geom.A, H))
+        self.exchanger = exchanger if exchanger is not None else (DistExchanger() if world > 1 else None)
+        self._overflow = torch.zeros(1, dtype=torch.int32, device=self.local._cuda)
+        self.steps_done = 0
+
+    # ------------------------------------------------------------------ fields
+    def full(self, name):
+        """Contiguous [local rows, pitch] tensor of the live copy of u / v / d / p (ghost rows and padding included)."""
+        ns, L = self.local, self.local._layout
+        k = {"density": "d"}.get(name, name)
+        cur = getattr(ns._state, "cur_" + k)
+        fname = "%s%d" % (k, cur)
+        rows, _, pitch = L.shape_of(fname)
+        off = L.offset[fname]
+        return ns._arena[off: off + rows * pitch].view(rows, pitch)
+
+    def _kind(self, name):
+        return "u" if name == "u" else "c"
+
+    def owned(self, name):
+        """View of the rows this rank owns, [rows, cols]."""
+        lo, hi = self.geom.owned_rows(self._kind(name))
+        cols = {"u": self.geom.W, "v": self.geom.W + 1}.get(name, self.geom.W)
+        return self.full(name)[lo:hi, :cols]
+
+    def scatter(self, name, global_field):
+        """Fill the stored rows (owned + ghosts) of a field from the global [rows, cols] array."""
+        g = torch.as_tensor(global_field, dtype=torch.float32)
+        rows = self.geom.rows(self._kind(name))
+        dst = self.full(name)
+        dst[:, :g.shape[1]].copy_(g[self.geom.A: self.geom.A + rows].to(dst.device))
+
+    def add_smoke_source(self, x, y, radius=10, intensity=1.0):
+        """navier_stokes.py:37-48 with the centre given in global coordinates."""
+        self.local.add_smoke_source(x, int(y) - self.geom.A, radius, intensity)
+
+    def setup_grid(self):
+        self.local.setup_grid()
+        self._overflow.zero_()
+
+    # ------------------------------------------------------------------ the step, phase by phase
+    def _g(self):
+        return C.byref(self.local._grid)
+
+    def _fdd(self):
+        ns = self.local
+        st, prm = ns._state, ns._params()
+        cu, cv, cd = st.cur_u, st.cur_v, st.cur_d
+        _lib.call("smk_forces_diffuse_div", self._g(), st.u[cu], st.v[cv], st.d[cd], st.u[cu ^ 1], st.v[cv ^ 1], st.d[cd ^ 1],
+                  st.div, prm.dt, prm.c_uv, prm.c_d, ns._stream())
+        st.cur_u, st.cur_v, st.cur_d = cu ^ 1, cv ^ 1, cd ^ 1
+
+    def _jacobi(self, t):
+        ns = self.local
+        st = ns._state
+        flag = C.c_int32(0)
+        _lib.call("smk_jacobi", self._g(), st.div, st.p[st.cur_p], st.p[st.cur_p ^ 1], int(t), int(t), C.byref(flag), ns._stream())
+        st.cur_p ^= flag.value
+
+    def _check(self, rows):
+        g = self.geom
+        if self.world == 1:
+            return None
+        lo = 0 if g.top_edge else 2
+        hi = rows if g.bottom_edge else rows - 2
+        return SlabCheck(g.own_lo, min(g.own_hi + 1, rows), lo, hi, self._overflow.data_ptr())
+
+    def _project_advect(self):
+        ns, g = self.local, self.geom
+        st, prm, L = ns._state, ns._params(), ns._layout
+        s = ns._stream()
+        _lib.call("smk_project", self._g(), st.p[st.cur_p], st.u[st.cur_u], st.v[st.cur_v], prm.dt, s)
+
+        def adv(k, rows, cols, pitch, scale):
+            arr, cur = getattr(st, k), getattr(st, "cur_" + k)
+            chk = self._check(rows)
+            _lib.call("smk_advect_slab", self._g(), arr[cur], arr[cur ^ 1], rows, cols, pitch, st.u[st.cur_u], st.v[st.cur_v],
+                      prm.dt, scale, C.byref(chk) if chk is not None else None, s)
+            setattr(st, "cur_" + k, cur ^ 1)
+        adv("u", g.hl + 1, g.W, L.pitch_u, 1.0)          # navier_stokes.py:166
+        adv("v", g.hl, g.W + 1, L.pitch_v, 1.0)          # :167 (uses the new u)
+        adv("d", g.hl, g.W, L.pitch_c, prm.decay)        # :168, :171
+        self.steps_done += 1
+
+    def step_plan(self):
+        """The step as a list of ("x", field names) halo exchanges and ("c", callable) compute phases."""
+        plan = []
+        if self.world > 1:
+            plan.append(("x", ("u", "v", "d")))
+        plan.append(("c", self._fdd))
+        for t in sweep_split(self.jacobi_iters, self.T):
+            plan.append(("c", (lambda t=t: self._jacobi(t))))
+            if self.world > 1:
+                plan.append(("x", ("p",)))
+        plan.append(("c", self._project_advect))
+        return plan
+
+    def exchange_list(self, names):
+        return [(self.full(n), self._kind(n)) for n in names]
+
+    def step(self):
+        """One time step of this rank's slab (all ranks must call it together)."""
+        for kind, arg in self.step_plan():
+            if kind == "x":
+                self.exchanger.exchange(self.geom, self.exchange_list(arg))
+            else:
+                arg()
+
+    def check(self):
+        """Raise if an advection back-trace ever left the rows this slab holds exactly (synchronises)."""
+        if int(self._overflow.item()) != 0:
+            raise RuntimeError("slab halo of %d rows is too shallow for the velocities reached (|dt*v| > %d rows): "
+                               "results near the slab boundary are not exact; use a deeper halo" % (self.halo, self.halo - 4))
+
+    def gather(self, name):
+        """All ranks: the global field assembled from every rank's owned rows (torch.distributed all_gather)."""
+        import torch.distributed as dist
+        mine = self.owned(name).contiguous()
+        if self.world == 1:
+            return mine.clone()
+        kind = self._kind(name)
+        sizes = []
+        for r, (r0, r1) in enumerate(self.geom.splits):
+            sizes.append(r1 - r0 + (1 if kind == "u" and r == self.world - 1 else 0))
+        mx = max(sizes)
+        pad = torch.zeros(mx, mine.shape[1], dtype=mine.dtype, device=mine.device)
+        pad[:mine.shape[0]] = mine
+        bufs = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(bufs, pad)
+        return torch.cat([b[:n] for b, n in zip(bufs, sizes)], dim=0)
+
+
+class LocalGroup:
+    """All `world` slabs of one grid in this process on one GPU, stepped in lockstep with in-process halo
+    copies: the single-GPU emulation of the multi-GPU run (tests; bit-identical to the undecomposed solver)."""
+
+    def __init__(self, grid_size, dt=0.01, viscosity=0.001, device="cuda", *, world, jacobi_iters=20, sweeps_per_launch=10, halo=None):
+        self.slabs = [SlabNavierStokes(grid_size, dt, viscosity, device, rank=r, world=world, jacobi_iters=jacobi_iters,
+                                       sweeps_per_launch=sweeps_per_launch, halo=halo, exchanger=False) for r in range(world)]
+        self.world = world
+
+    def scatter(self, name, global_field):
+        for s in self.slabs:
+            s.scatter(name, global_field)
+
+    def add_smoke_source(self, x, y, radius=10, intensity=1.0):
+        for s in self.slabs:
+            s.add_smoke_source(x, y, radius, intensity)
+
+    def step(self):
+        plans = [s.step_plan() for s in self.slabs]
+        for k in range(len(plans[0])):
+            kind = plans[0][k][0]
+            if kind == "x":
+                names = plans[0][k][1]
+                local_exchange([s.geom for s in self.slabs], [s.exchange_list(names) for s in self.slabs])
+            else:
+                for p in plans:
+                    p[k][1]()
+
+    def gather(self, name):
+        return torch.cat([s.owned(name) for s in self.slabs], dim=0)
+
+    def check(self):
+        for s in self.slabs:
+            s.check()

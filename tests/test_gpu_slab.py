@@ -1,0 +1,129 @@
+"""GPU tests of the row-slab decomposition: every slab of a grid on ONE GPU with in-process halo copies
+(LocalGroup) must reproduce the undecomposed CUDA solver -- and therefore the reference -- bit for bit;
+with two or more GPUs the same through NCCL send/recv."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import assert_same
+from test_slab_host import random_state, reference_run
+
+pytestmark = pytest.mark.gpu
+
+from smokephysai_b200 import NavierStokesSimulator  # noqa: E402
+from smokephysai_b200.slab import LocalGroup, SlabNavierStokes  # noqa: E402
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("world,K,T,H,W", [(2, 20, 10, 96, 40), (3, 13, 4, 90, 133), (4, 24, 8, 300, 260), (8, 20, 10, 1024, 512)])
+def test_local_group_matches_undecomposed(world, K, T, H, W):
+    dt, nu, steps = 0.02, 0.01, 3
+    st0 = random_state(H, W, seed=world * 7 + K)
+    whole = NavierStokesSimulator((H, W), dt, nu, "cuda", jacobi_iters=K)
+    grp = LocalGroup((H, W), dt, nu, "cuda", world=world, jacobi_iters=K, sweeps_per_launch=T)
+    for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+        setattr(whole, name, torch.from_numpy(st0[k]).cuda())
+        grp.scatter(k, st0[k])
+    for _ in range(steps):
+        whole.step()
+        grp.step()
+    grp.check()
+    for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+        cols = st0[k].shape[1]
+        assert_same(N(grp.gather(k))[:, :cols], N(getattr(whole, name)), "%s world %d" % (k, world))
+    if H <= 128:                                              # and against the oracle directly
+        want = reference_run(st0, dt, nu, K, steps)
+        assert_same(N(grp.gather("d"))[:, :W], want["d"], "density vs oracle")
+
+
+def test_slab_sources_and_emitter_scenario():
+    """Emitters given in global coordinates land on the right slab rows; 5 steps equal the whole-grid run."""
+    H = W = 256
+    whole = NavierStokesSimulator((H, W), device="cuda", jacobi_iters=20)
+    grp = LocalGroup((H, W), device="cuda", world=4, jacobi_iters=20, sweeps_per_launch=10)
+    for x, y, i in ((64, 60, 1.5), (130, 128, 1.0), (200, 190, 0.8), (30, 250, 1.2)):
+        whole.add_smoke_source(x, y, radius=8, intensity=i)
+        grp.add_smoke_source(x, y, radius=8, intensity=i)
+    assert_same(N(grp.gather("d"))[:, :W], N(whole.density), "initial density")
+    for _ in range(5):
+        whole.step()
+        grp.step()
+    for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+        assert_same(N(grp.gather(k))[:, :N(getattr(whole, name)).shape[1]], N(getattr(whole, name)), k)
+
+
+def test_overflow_guard_trips_on_huge_velocity():
+    H, W = 128, 64
+    grp = LocalGroup((H, W), 0.02, 0.01, "cuda", world=2, jacobi_iters=4, sweeps_per_launch=4)      # halo 8
+    st0 = random_state(H, W, seed=1, vel=4000.0)                                                       # |dt*v| up to 40 rows
+    for k in ("u", "v", "p", "d"):
+        grp.scatter(k, st0[k])
+    grp.step()
+    with pytest.raises(RuntimeError, match="halo"):
+        grp.check()
+
+
+def test_single_rank_slab_is_the_plain_solver():
+    H, W = 64, 48
+    st0 = random_state(H, W, seed=5)
+    one = SlabNavierStokes((H, W), 0.02, 0.01, "cuda", rank=0, world=1, jacobi_iters=10)
+    whole = NavierStokesSimulator((H, W), 0.02, 0.01, "cuda", jacobi_iters=10)
+    for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+        one.scatter(k, st0[k])
+        setattr(whole, name, torch.from_numpy(st0[k]).cuda())
+    for _ in range(2):
+        one.step()
+        whole.step()
+    for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+        assert_same(N(one.gather(k)), N(getattr(whole, name)), k)
+
+
+# --------------------------------------------------------------------------- real NCCL, needs >= 2 GPUs
+def _nccl_worker(rank, world, port, H, W, K, T, steps, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        st0 = random_state(H, W, seed=21)
+        slab = SlabNavierStokes((H, W), 0.02, 0.01, "cuda:%d" % rank, rank=rank, world=world, jacobi_iters=K, sweeps_per_launch=T)
+        for k in ("u", "v", "p", "d"):
+            slab.scatter(k, st0[k])
+        for _ in range(steps):
+            slab.step()
+        slab.check()
+        full = {k: slab.gather(k).cpu().numpy() for k in ("u", "v", "p", "d")}
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "gathered.npz"), **full)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_nccl_slabs_match_undecomposed(tmp_path):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    H, W, K, T, steps = 512, 384, 20, 10, 3
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_nccl_worker, args=(world, port, H, W, K, T, steps, str(tmp_path)), nprocs=world, join=True)
+    st0 = random_state(H, W, seed=21)
+    whole = NavierStokesSimulator((H, W), 0.02, 0.01, "cuda", jacobi_iters=K)
+    for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+        setattr(whole, name, torch.from_numpy(st0[k]).cuda())
+    for _ in range(steps):
+        whole.step()
+    got = np.load(os.path.join(str(tmp_path), "gathered.npz"))
+    for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+        ref = N(getattr(whole, name))
+        assert_same(got[k][:, :ref.shape[1]], ref, "%s over NCCL, world %d" % (k, world))
