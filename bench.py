@@ -44,6 +44,9 @@ WORKLOADS = {
                     "20 steps/sequence (BASELINE.json configs[1])"),
     "c3": dict(h=1024, w=1024, batch=1, K=100, tsteps=20,
                name="c3: single 1024x1024 grid, 100 Jacobi sweeps/step, 20 steps (BASELINE.json configs[2])"),
+    "c4": dict(h=8192, w=8192, batch=1, K=20, tsteps=5,
+               name="c4: single 8192x8192 grid, 20 Jacobi sweeps/step, 5 steps per bench step, row slabs over the GPUs "
+                    "(BASELINE.json configs[3]; strong scaling)"),
 }
 
 # algorithmic bytes per cell per launch of each kernel family (fp32, each array touched once)
@@ -153,7 +156,10 @@ def cpu_run(wl, nseq, nthreads, seq0=0):
     p = np.zeros((nseq, h, w), np.float32); d = np.zeros((nseq, h, w), np.float32)
     for s in range(nseq):
         for x, y, r, i in emitters_for_sequence(seq0 + s, h, w):
-            oracle.splat(d[s], x, y, r, i)
+            y0, y1, x0, x1 = max(0, y - r), min(h, y + r + 1), max(0, x - r), min(w, x + r + 1)
+            sub = np.ascontiguousarray(d[s, y0:y1, x0:x1])          # the splat only touches the emitter's bounding box
+            oracle.splat(sub, x - x0, y - y0, r, i)
+            d[s, y0:y1, x0:x1] = sub
     fmul = oracle.fractal_mul(h, 0.05) if h == w else None
     t0 = time.perf_counter()
     oracle.run_batch(u, v, p, d, 0.01, 0.001, K, T, fmul=fmul, want_frames=True, nthreads=nthreads)
@@ -176,7 +182,7 @@ def reference_arm(args, wl):
     nseq = cpu_sample_size(wl)
     wl_cpu = dict(wl)
     if wl["h"] >= 1024:
-        wl_cpu["tsteps"] = 2
+        wl_cpu["tsteps"] = 2 if wl["h"] < 4096 else 1
     for _ in range(args.warmup):
         cpu_run(wl_cpu, nseq, cores)
     t_tot, cells = 0.0, 0
@@ -192,7 +198,7 @@ def reference_arm(args, wl):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "host": "rank 0 only; oracle/ C port of the reference step (the reference is pure "
                    "Python/PyTorch and publishes no number for this path), pthreads over sequences"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": min(cores, nseq), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -244,20 +250,64 @@ def main():
         return float(t.item())
 
     h, w, B, K, T = wl["h"], wl["w"], wl["batch"], wl["K"], wl["tsteps"]
-    sim = SmokeSimulator((h, w), 0.01, 0.001, dev, jacobi_iters=K, batch=B, sweeps_per_launch=args.sweeps_per_launch)
-    ns = sim.ns_solver
-    L = ns._layout
-    ems = [emitters_for_sequence(rank * B + s, h, w) for s in range(B)]
-    fmul = sim.fractal_gen.multiplier((h, w), 0.05)
-    frames = torch.empty(B, T, h, L.pitch_c, dtype=torch.float32, device=dev)
-    src, off, h2d_bytes = ns.upload_sources(ems)
-    cells_per_step_rank = B * h * w * T
-    working_set = ns._arena.numel() * 4 + frames.numel() * 4
+    slab_mode = args.workload == "c4"
+    if not slab_mode:
+        sim = SmokeSimulator((h, w), 0.01, 0.001, dev, jacobi_iters=K, batch=B, sweeps_per_launch=args.sweeps_per_launch)
+        ns = sim.ns_solver
+        L = ns._layout
+        ems = [emitters_for_sequence(rank * B + s, h, w) for s in range(B)]
+        fmul = sim.fractal_gen.multiplier((h, w), 0.05)
+        frames = torch.empty(B, T, h, L.pitch_c, dtype=torch.float32, device=dev)
+        src, off, h2d_bytes = ns.upload_sources(ems)
+        cells_per_step_rank = B * h * w * T
+        cells_per_launch = B * h * w
+        working_set = ns._arena.numel() * 4 + frames.numel() * 4
+        emitter_lists = [[((x, y), i) for x, y, _, i in lst] for lst in ems]
 
-    def device_step():
-        ns.setup_grid()
-        ns.splat_uploaded(src, off)
-        ns.run_steps(T, fmul=fmul, out=frames)
+        def device_step():
+            ns.setup_grid()
+            ns.splat_uploaded(src, off)
+            ns.run_steps(T, fmul=fmul, out=frames)
+
+        def e2e_step():
+            return sim.generate_sequences(emitter_lists, T, to_host=True)      # returns after the last D2H copy
+
+        d2h_bytes = T * B * h * L.pitch_c * 4
+        e2e_api = "SmokeSimulator.generate_sequences(host emitter lists, to_host=True) -> pinned host frames"
+        scaling = "weak"
+        total_cells_per_step = world * cells_per_step_rank
+        parallelism = "sequences sharded over %d GPU(s), no data-path collective" % world
+    else:
+        from smokephysai_b200.slab import SlabNavierStokes
+        Tj = args.sweeps_per_launch or 10
+        slab = SlabNavierStokes((h, w), 0.01, 0.001, dev, rank=rank, world=world, jacobi_iters=K, sweeps_per_launch=Tj)
+        ems = emitters_for_sequence(0, h, w)
+        slab.add_sources(ems)
+        cells_per_step_rank = (slab.geom.R1 - slab.geom.R0) * w * T
+        cells_per_launch = slab.geom.hl * w
+        working_set = slab.local._arena.numel() * 4
+        h2d_bytes = 16 * len(ems) + 8
+        host_d = torch.empty(slab.geom.R1 - slab.geom.R0, w, dtype=torch.float32).pin_memory()
+
+        def device_step():
+            for _ in range(T):
+                slab.step()
+
+        def e2e_step():
+            slab.setup_grid()
+            slab.add_sources(ems)
+            for _ in range(T):
+                slab.step()
+            host_d.copy_(slab.owned("d"), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return host_d.unsqueeze(0)
+
+        d2h_bytes = host_d.numel() * 4
+        e2e_api = "SlabNavierStokes: setup_grid + add_sources(host list) + %d x step() + owned density rows -> pinned host" % T
+        scaling = "strong"
+        total_cells_per_step = h * w * T
+        parallelism = ("row slabs over %d GPU(s), halo %d rows, NCCL send/recv of p after every launch of <= %d fused sweeps "
+                       "and of u,v,density once per step" % (world, slab.halo, Tj)) if world > 1 else "single GPU, undecomposed"
 
     # ---- device-resident throughput -----------------------------------------------------------------
     for _ in range(args.warmup):
@@ -277,7 +327,7 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - n0
     clk = clocks.stop() if rank == 0 else None
-    value = world * cells_per_step_rank * args.steps / (ms * 1e-3)
+    value = total_cells_per_step * args.steps / (ms * 1e-3)
 
     # ---- per-kernel shares (second pass over the same steps, events around every launch) ------------------
     barrier()
@@ -287,20 +337,20 @@ def main():
     torch.cuda.synchronize()
     prof = _lib.profile_end()
 
-    # ---- end to end through the public API: host emitter lists -> frames in pinned host memory ------------
-    emitter_lists = [[((x, y), i) for x, y, _, i in lst] for lst in ems]
+    # ---- end to end through the public API: host emitter lists -> results in pinned host memory ------------
     for _ in range(2):
-        host_frames = sim.generate_sequences(emitter_lists, T, to_host=True)
+        host_frames = e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        host_frames = sim.generate_sequences(emitter_lists, T, to_host=True)      # returns after the last D2H copy
+        host_frames = e2e_step()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e_value = world * cells_per_step_rank * args.steps / e2e_s
-    d2h_bytes = T * B * h * L.pitch_c * 4
+    e2e_value = total_cells_per_step * args.steps / e2e_s
     checksum = float(host_frames[:, -1].double().sum())
+    if slab_mode:
+        slab.check()
 
     if world > 1:
         dist.destroy_process_group()
@@ -314,7 +364,7 @@ def main():
     total_prof_ms = sum(v[0] for v in prof.values())
     sweeps_in_launch = K * T * args.steps / dom_n if dom == "jacobi" else 0
     bpc = phase_bytes_per_cell(K, sweeps_in_launch)
-    alg_bytes_per_launch = bpc[dom] * B * h * w
+    alg_bytes_per_launch = bpc[dom] * cells_per_launch
     achieved = alg_bytes_per_launch / (dom_ms / dom_n * 1e-3) / 1e9
     kernel_name = {"jacobi": "k_jacobi", "forces_diffuse_div": "k_forces_diffuse_div", "project": "k_project",
                    "advect_u": "k_advect", "advect_v": "k_advect", "advect_d": "k_advect", "splat": "k_splat"}.get(dom, dom)
@@ -329,19 +379,19 @@ def main():
     step_bytes = 100 + 12 * K
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "grid": [h, w], "sequences_per_gpu": B, "jacobi_iters": K, "time_steps_per_bench_step": T,
-                   "parallelism": "sequences sharded over %d GPU(s), no data-path collective" % world,
+                   "parallelism": parallelism,
                    "l2": "no flush: working set %.0f MB per GPU (fields + frames) > 126 MB L2" % (working_set / 1e6)},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": 1e3 * e2e_s / args.steps, "api": "SmokeSimulator.generate_sequences(host emitter lists) -> pinned host frames",
+                "ms_per_step": 1e3 * e2e_s / args.steps, "api": e2e_api,
                 "last_frame_checksum": checksum},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_step": {"algorithmic_bytes_per_cell_step": step_bytes, "achieved": value / world * step_bytes / 1e9, "peak": peak,
-                          "unit": "GB/s", "frac": value / world * step_bytes / 1e9 / peak, "per": "GPU"},
+                          "unit": "GB/s", "frac": value / world * step_bytes / 1e9 / peak, "per": "GPU (owned cells only; ghost-row recompute not counted)"},
         "phases_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
     }
     if not args.no_cpu_baseline:
@@ -351,10 +401,10 @@ def main():
         nseq = cpu_sample_size(wl)
         wl_cpu = dict(wl)
         if h >= 1024:
-            wl_cpu["tsteps"] = 2
+            wl_cpu["tsteps"] = 2 if h < 4096 else 1
         cpu_run(wl_cpu, min(nseq, cores), cores)                 # warm the threads / page in
         cval, cdt = cpu_run(wl_cpu, nseq, cores)
-        out["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port", "seconds": cdt,
+        out["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": min(cores, nseq), "kind": "port", "seconds": cdt,
                                "sample": "%d sequences x %d steps of %dx%d, K=%d (oracle C port, pthreads over sequences)"
                                          % (nseq, wl_cpu["tsteps"], h, w, K)}
     print(json.dumps(out))

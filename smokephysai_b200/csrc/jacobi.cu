@@ -22,30 +22,51 @@
 
 namespace smk {
 
-template <int R, bool FAST>
-__device__ __forceinline__ void sweep_rows(float4 (&P)[R], const float4 (&D)[R], float4 up, const float4 dnh,
-                                           const float cm0, const float cm1, const float cm2, const float cm3,
-                                           const int gi0, const int h)
+// One row of four cells: m * ((((up + dn) + left) + right) - div), left/right neighbours of the strip by shuffle.
+__device__ __forceinline__ float4 stencil_row(const float4 up, const float4 cur, const float4 dn, const float4 d,
+                                              const float m0, const float m1, const float m2, const float m3)
 {
+    const float left = __shfl_up_sync(0xffffffffu, cur.w, 1);
+    const float right = __shfl_down_sync(0xffffffffu, cur.x, 1);
+    float4 nw;
+    nw.x = m0 * ((((up.x + dn.x) + left) + cur.y) - d.x);
+    nw.y = m1 * ((((up.y + dn.y) + cur.x) + cur.z) - d.y);
+    nw.z = m2 * ((((up.z + dn.z) + cur.y) + cur.w) - d.z);
+    nw.w = m3 * ((((up.w + dn.w) + cur.z) + right) - d.w);
+    return nw;
+}
+
+// One sweep of a warp's R x 128 strip, boundary rows first: the new first and last rows are what the
+// neighbouring warps need for the NEXT sweep, so they are computed and posted to shared memory before the
+// R-2 interior rows; the CTA barrier that publishes them then overlaps with the interior arithmetic.
+template <int R, bool FAST>
+__device__ __forceinline__ void sweep_rows(float4 (&P)[R], const float4 (&D)[R], const float4 uph, const float4 dnh,
+                                           const float cm0, const float cm1, const float cm2, const float cm3,
+                                           const int gi0, const int h, float4* post_first, float4* post_last)
+{
+    auto rowok = [&](int r) { const int gi = gi0 + r; return FAST || (gi >= 1 && gi <= h - 2); };
+    const float4 o0 = P[0], oL = P[R - 1];
+    float4 n0, nL;
+    {
+        const bool ok = rowok(0);
+        n0 = stencil_row(uph, o0, R > 1 ? P[1] : dnh, D[0], ok ? cm0 : 0.f, ok ? cm1 : 0.f, ok ? cm2 : 0.f, ok ? cm3 : 0.f);
+    }
+    if (R > 1) {
+        const bool ok = rowok(R - 1);
+        nL = stencil_row(P[R - 2], oL, dnh, D[R - 1], ok ? cm0 : 0.f, ok ? cm1 : 0.f, ok ? cm2 : 0.f, ok ? cm3 : 0.f);
+    } else nL = n0;
+    if (post_first) { *post_first = n0; *post_last = nL; }
+    float4 up = o0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int r = 1; r < R - 1; ++r) {
         const float4 cur = P[r];
-        const float4 dn = (r < R - 1) ? P[r + 1] : dnh;
-        const float left = __shfl_up_sync(0xffffffffu, cur.w, 1);
-        const float right = __shfl_down_sync(0xffffffffu, cur.x, 1);
-        float m0 = cm0, m1 = cm1, m2 = cm2, m3 = cm3;
-        if (!FAST) {
-            const int gi = gi0 + r;
-            if (gi < 1 || gi > h - 2) { m0 = 0.f; m1 = 0.f; m2 = 0.f; m3 = 0.f; }
-        }
-        float4 nw;
-        nw.x = m0 * ((((up.x + dn.x) + left) + cur.y) - D[r].x);
-        nw.y = m1 * ((((up.y + dn.y) + cur.x) + cur.z) - D[r].y);
-        nw.z = m2 * ((((up.z + dn.z) + cur.y) + cur.w) - D[r].z);
-        nw.w = m3 * ((((up.w + dn.w) + cur.z) + right) - D[r].w);
-        P[r] = nw;
+        const float4 dn = (r < R - 2) ? P[r + 1] : oL;
+        const bool ok = rowok(r);
+        P[r] = stencil_row(up, cur, dn, D[r], ok ? cm0 : 0.f, ok ? cm1 : 0.f, ok ? cm2 : 0.f, ok ? cm3 : 0.f);
         up = cur;
     }
+    P[0] = n0;
+    if (R > 1) P[R - 1] = nL;
 }
 
 template <int R, int NW>
@@ -83,15 +104,18 @@ k_jacobi(const float* __restrict__ pin, float* __restrict__ pout, const float* _
     const bool fast = (gi0 >= 1) && (gi0 + R - 1 <= h - 2);     // warp-uniform: no ring row in this warp
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    halo[0][0][warp][lane] = P[0];
+    halo[0][1][warp][lane] = P[R - 1];
+    __syncthreads();
     for (int s = 0; s < T; ++s) {
         const int buf = s & 1;
-        halo[buf][0][warp][lane] = P[0];
-        halo[buf][1][warp][lane] = P[R - 1];
-        __syncthreads();
         const float4 up = warp > 0 ? halo[buf][1][warp - 1][lane] : zero4;
         const float4 dn = warp < NW - 1 ? halo[buf][0][warp + 1][lane] : zero4;
-        if (fast) sweep_rows<R, true>(P, D, up, dn, cm0, cm1, cm2, cm3, gi0, h);
-        else      sweep_rows<R, false>(P, D, up, dn, cm0, cm1, cm2, cm3, gi0, h);
+        float4* pf = (s + 1 < T) ? &halo[buf ^ 1][0][warp][lane] : nullptr;
+        float4* pl = (s + 1 < T) ? &halo[buf ^ 1][1][warp][lane] : nullptr;
+        if (fast) sweep_rows<R, true>(P, D, up, dn, cm0, cm1, cm2, cm3, gi0, h, pf, pl);
+        else      sweep_rows<R, false>(P, D, up, dn, cm0, cm1, cm2, cm3, gi0, h, pf, pl);
+        if (s + 1 < T) __syncthreads();
     }
 
     // store the part of the tile that is still exact after T sweeps
@@ -105,6 +129,130 @@ k_jacobi(const float* __restrict__ pin, float* __restrict__ pout, const float* _
             const int gi = gi0 + r;
             if (gi >= vy0 && gi < vy1 && gi < h)
                 *reinterpret_cast<float4*>(pout + (size_t)gi * pitch + gj) = P[r];
+        }
+    }
+}
+
+// Packed variant (sm_100 add.f32x2 / mul.f32x2 through __fadd2_rn / __fmul2_rn: two IEEE-rounded fp32 results
+// per instruction, so half the issue slots for the same arithmetic).  A float2 pairs row rr of the warp's strip
+// with row rr + R/2, which keeps every stencil neighbour of a pair aligned in another pair (up of (rr, rr+R/2) is
+// (rr-1, rr-1+R/2)); only the seam between the two half strips needs a repack per sweep.  x - d is x + (-d), so
+// the divergence is held negated.  The Dirichlet ring / out-of-domain rows are zeroed after the sweep (ringmask).
+template <int R>
+struct PackedStrip {
+    float2 Q[R / 2][4];      // pressure: Q[rr][c] = (p[rr][c], p[rr + R/2][c])
+    float2 ND[R / 2][4];     // minus divergence, same pairing
+};
+
+template <int R>
+__device__ __forceinline__ void sweep_rows_packed(PackedStrip<R>& S, const float4 uph, const float4 dnh,
+                                                  const float2 (&M)[4], const unsigned ringmask)
+{
+    constexpr int H = R / 2;
+    // seam pairs: up of row 0 / row H, down of row H-1 / row R-1
+    float2 up[4] = {make_float2(uph.x, S.Q[H - 1][0].x), make_float2(uph.y, S.Q[H - 1][1].x),
+                    make_float2(uph.z, S.Q[H - 1][2].x), make_float2(uph.w, S.Q[H - 1][3].x)};
+    const float2 dnl[4] = {make_float2(S.Q[0][0].y, dnh.x), make_float2(S.Q[0][1].y, dnh.y),
+                           make_float2(S.Q[0][2].y, dnh.z), make_float2(S.Q[0][3].y, dnh.w)};
+#pragma unroll
+    for (int rr = 0; rr < H; ++rr) {
+        float2 cur[4] = {S.Q[rr][0], S.Q[rr][1], S.Q[rr][2], S.Q[rr][3]};
+        float2 left, right;
+        left.x = __shfl_up_sync(0xffffffffu, cur[3].x, 1);
+        left.y = __shfl_up_sync(0xffffffffu, cur[3].y, 1);
+        right.x = __shfl_down_sync(0xffffffffu, cur[0].x, 1);
+        right.y = __shfl_down_sync(0xffffffffu, cur[0].y, 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float2 dn = (rr < H - 1) ? S.Q[rr + 1][c] : dnl[c];
+            const float2 l = (c == 0) ? left : cur[c - 1];
+            const float2 r = (c == 3) ? right : cur[c + 1];
+            float2 t = __fadd2_rn(up[c], dn);
+            t = __fadd2_rn(t, l);
+            t = __fadd2_rn(t, r);
+            t = __fadd2_rn(t, S.ND[rr][c]);
+            S.Q[rr][c] = __fmul2_rn(M[c], t);
+            up[c] = cur[c];
+        }
+    }
+    if (ringmask) {
+#pragma unroll
+        for (int rr = 0; rr < H; ++rr) {
+            if (ringmask & (1u << rr)) { S.Q[rr][0].x = 0.f; S.Q[rr][1].x = 0.f; S.Q[rr][2].x = 0.f; S.Q[rr][3].x = 0.f; }
+            if (ringmask & (1u << (rr + H))) { S.Q[rr][0].y = 0.f; S.Q[rr][1].y = 0.f; S.Q[rr][2].y = 0.f; S.Q[rr][3].y = 0.f; }
+        }
+    }
+}
+
+template <int R, int NW>
+__global__ void __launch_bounds__(NW * 32, (NW * 32 <= 256) ? 2 : 1)
+k_jacobi_packed(const float* __restrict__ pin, float* __restrict__ pout, const float* __restrict__ div,
+                const int h, const int w, const int pitch, const long long bstride,
+                const int T, const int HX, const int ox, const int oy)
+{
+    constexpr int H = R / 2;
+    __shared__ float4 halo[2][2][NW][32];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * ox, y0 = blockIdx.y * oy;
+    const int gj = x0 + lane * 4;
+    const int gi0 = y0 + warp * R;
+    const size_t boff = (size_t)blockIdx.z * (size_t)bstride;
+    pin += boff; pout += boff; div += boff;
+
+    PackedStrip<R> S;
+    const bool colin = gj < pitch;
+    unsigned ringmask = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int gi = gi0 + r;
+        float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = p4;
+        if (colin && gi < h) {
+            p4 = *reinterpret_cast<const float4*>(pin + (size_t)gi * pitch + gj);
+            d4 = __ldg(reinterpret_cast<const float4*>(div + (size_t)gi * pitch + gj));
+        }
+        if (gi < 1 || gi > h - 2) ringmask |= 1u << r;
+        const int rr = r % H;
+        if (r < H) {
+            S.Q[rr][0].x = p4.x; S.Q[rr][1].x = p4.y; S.Q[rr][2].x = p4.z; S.Q[rr][3].x = p4.w;
+            S.ND[rr][0].x = -d4.x; S.ND[rr][1].x = -d4.y; S.ND[rr][2].x = -d4.z; S.ND[rr][3].x = -d4.w;
+        } else {
+            S.Q[rr][0].y = p4.x; S.Q[rr][1].y = p4.y; S.Q[rr][2].y = p4.z; S.Q[rr][3].y = p4.w;
+            S.ND[rr][0].y = -d4.x; S.ND[rr][1].y = -d4.y; S.ND[rr][2].y = -d4.z; S.ND[rr][3].y = -d4.w;
+        }
+    }
+    float2 M[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float m = (gj + c >= 1 && gj + c <= w - 2) ? 0.25f : 0.f;
+        M[c] = make_float2(m, m);
+    }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int s = 0; s < T; ++s) {
+        const int buf = s & 1;
+        halo[buf][0][warp][lane] = make_float4(S.Q[0][0].x, S.Q[0][1].x, S.Q[0][2].x, S.Q[0][3].x);                       // row 0
+        halo[buf][1][warp][lane] = make_float4(S.Q[H - 1][0].y, S.Q[H - 1][1].y, S.Q[H - 1][2].y, S.Q[H - 1][3].y);       // row R-1
+        __syncthreads();
+        const float4 up = warp > 0 ? halo[buf][1][warp - 1][lane] : zero4;
+        const float4 dn = warp < NW - 1 ? halo[buf][0][warp + 1][lane] : zero4;
+        sweep_rows_packed<R>(S, up, dn, M, ringmask);
+    }
+
+    const int vx0 = x0 + (blockIdx.x > 0 ? HX : 0);
+    const int vx1 = (blockIdx.x + 1 < gridDim.x) ? x0 + 128 - HX : pitch;
+    const int vy0 = y0 + (blockIdx.y > 0 ? T : 0);
+    const int vy1 = (blockIdx.y + 1 < gridDim.y) ? y0 + NW * R - T : h;
+    if (gj >= vx0 && gj < vx1 && gj < pitch) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int gi = gi0 + r;
+            const int rr = r % H;
+            if (gi >= vy0 && gi < vy1 && gi < h) {
+                const float4 o = (r < H) ? make_float4(S.Q[rr][0].x, S.Q[rr][1].x, S.Q[rr][2].x, S.Q[rr][3].x)
+                                         : make_float4(S.Q[rr][0].y, S.Q[rr][1].y, S.Q[rr][2].y, S.Q[rr][3].y);
+                *reinterpret_cast<float4*>(pout + (size_t)gi * pitch + gj) = o;
+            }
         }
     }
 }
@@ -143,6 +291,13 @@ static int pick_T(const smk_grid_t* g, int K, int TH, int tmax, int sms)
     return bestT;
 }
 
+static bool use_packed()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SMK_JACOBI_PACKED"); v = e ? atoi(e) : 0; }
+    return v != 0;
+}
+
 template <int R, int NW>
 static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, int K, int T, int* in_scratch, cudaStream_t s)
 {
@@ -160,8 +315,12 @@ static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, in
         int rc;
         {
             ProfScope prof_(SMK_PH_JACOBI, s);
-            k_jacobi<R, NW><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c, (long long)g->stride_c,
-                                                     t, HX, 128 - 2 * HX, TH - 2 * t);
+            if (use_packed())
+                k_jacobi_packed<R, NW><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c, (long long)g->stride_c,
+                                                                t, HX, 128 - 2 * HX, TH - 2 * t);
+            else
+                k_jacobi<R, NW><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c, (long long)g->stride_c,
+                                                         t, HX, 128 - 2 * HX, TH - 2 * t);
             rc = check_launch("k_jacobi");
         }
         if (rc != SMK_OK) return rc;

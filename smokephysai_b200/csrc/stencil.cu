@@ -427,28 +427,55 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
 }
 
 // ---- a2: add_smoke_source, batched ---------------------------------------------------------------------
-__global__ void k_splat(float* __restrict__ Dn, const int h, const int w, const int pc, const long long sc_,
-                        const smk_source_t* __restrict__ src, const int32_t* __restrict__ off)
+// Cell-centric so that overlapping emitters are added in list order (fp32 addition is order dependent,
+// and the reference applies them one call after another).  A CTA owns a 32 x 8 tile; it first culls the
+// simulation's emitter list, 256 at a time, to those whose bounding box touches the tile (ordered
+// compaction with ballots), then every cell walks the short list.  Large grids carry thousands of emitters.
+__global__ void __launch_bounds__(256)
+k_splat(float* __restrict__ Dn, const int h, const int w, const int pc, const long long sc_,
+        const smk_source_t* __restrict__ src, const int32_t* __restrict__ off)
 {
-    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
-    if (i >= h || j >= w) return;
+    __shared__ int list[256];
+    __shared__ int wcount[8];
+    const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x, wp = threadIdx.y;
+    const int j0 = blockIdx.x * 32, i0 = blockIdx.y * 8;
+    const int j = j0 + lane, i = i0 + wp;
     const int b = blockIdx.z;
     const int s0 = off[b], s1 = off[b + 1];
     if (s0 == s1) return;
+    const bool in = i < h && j < w;
     float* cell = Dn + (size_t)b * sc_ + (size_t)i * pc + j;
-    float acc = *cell;
-    for (int k = s0; k < s1; ++k) {
-        const smk_source_t e = src[k];
-        const long long dx = (long long)j - e.x, dy = (long long)i - e.y;
-        const float dist = sqrtf((float)(dx * dx + dy * dy));            // navier_stokes.py:45
-        if (dist <= (float)e.radius) {                                   // :46
-            const double r3 = (double)e.radius / 3.0;
-            const float denom = (float)(2.0 * (r3 * r3));
-            const float d2 = dist * dist;
-            acc = acc + e.intensity * expf((-d2) / denom);               // :48
+    float acc = in ? *cell : 0.f;
+    for (int base = s0; base < s1; base += 256) {
+        const int k = base + tid;
+        bool hit = false;
+        if (k < s1) {
+            const smk_source_t e = src[k];
+            const long long r = e.radius;
+            hit = (long long)j0 <= e.x + r && (long long)j0 + 31 >= e.x - r && (long long)i0 <= e.y + r && (long long)i0 + 7 >= e.y - r;
         }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) wcount[wp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { if (q < wp) before += wcount[q]; total += wcount[q]; }
+        if (hit) list[before + __popc(m & ((1u << lane) - 1u))] = k;
+        __syncthreads();
+        for (int q = 0; q < total; ++q) {
+            const smk_source_t e = src[list[q]];
+            const long long dx = (long long)j - e.x, dy = (long long)i - e.y;
+            const float dist = sqrtf((float)(dx * dx + dy * dy));            // navier_stokes.py:45
+            if (dist <= (float)e.radius) {                                   // :46
+                const double r3 = (double)e.radius / 3.0;
+                const float denom = (float)(2.0 * (r3 * r3));
+                const float d2 = dist * dist;
+                acc = acc + e.intensity * expf((-d2) / denom);               // :48
+            }
+        }
+        __syncthreads();
     }
-    *cell = acc;
+    if (in) *cell = acc;
 }
 
 int launch_splat(const smk_grid_t* g, float* density, const smk_source_t* src, const int32_t* off, cudaStream_t s)

@@ -15,11 +15,15 @@ Host PyTorch is used for device memory and streams only; all arithmetic on the p
 """
 import ctypes as C
 
+import numpy as np
 import torch
 import torch.nn as nn
 
 from . import _lib
 from ._lib import Grid, Params, Source, State
+
+
+SOURCE_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("radius", "<i4"), ("intensity", "<f4")])     # smk_source_t
 
 
 def _round4(n):
@@ -211,9 +215,12 @@ class NavierStokesSimulator(nn.Module):
         for lst in per_sim:
             flat.extend(lst)
             offs.append(len(flat))
-        n = max(len(flat), 1)
-        arr = (Source * n)(*[Source(int(x), int(y), int(r), float(i)) for x, y, r, i in flat])
-        src_h = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        rec = np.zeros(max(len(flat), 1), dtype=SOURCE_DTYPE)          # smk_source_t records, 16 B each
+        if flat:
+            arr = np.asarray(flat, dtype=np.float64).reshape(len(flat), 4)
+            rec["x"], rec["y"], rec["radius"] = arr[:, 0].astype(np.int32), arr[:, 1].astype(np.int32), arr[:, 2].astype(np.int32)
+            rec["intensity"] = arr[:, 3].astype(np.float32)
+        src_h = torch.from_numpy(rec.view(np.uint8))
         off_h = torch.tensor(offs, dtype=torch.int32)
         if pin:
             src_h, off_h = src_h.pin_memory(), off_h.pin_memory()

@@ -189,6 +189,10 @@ class SlabNavierStokes:
         """navier_stokes.py:37-48 with the centre given in global coordinates."""
         self.local.add_smoke_source(x, int(y) - self.geom.A, radius, intensity)
 
+    def add_sources(self, sources):
+        """Ordered emitter list [(x, y, radius, intensity), ...] in global coordinates, one batched splat."""
+        self.local.add_sources([[(x, int(y) - self.geom.A, r, i) for x, y, r, i in sources]])
+
     def setup_grid(self):
         self.local.setup_grid()
         self._overflow.zero_()
