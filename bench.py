@@ -206,6 +206,40 @@ def reference_arm(args, wl):
     return 0
 
 
+def reference_torch_numbers(dev):
+    """Informational: the UNMODIFIED reference NavierStokesSimulator (installed in git-ignored baseline/_ref by
+    `pip install --no-deps --target baseline/_ref <copy of /root/reference>`) stepped on the host CPU and, eagerly,
+    on this GPU.  128x128, its hard-coded 20 Jacobi sweeps (navier_stokes.py:139), one sequence.  None if absent."""
+    path = os.path.join(ROOT, "baseline", "_ref", "src", "physics", "navier_stokes.py")
+    if not os.path.exists(path):
+        return None
+    try:
+        import importlib.util
+        import torch
+        spec = importlib.util.spec_from_file_location("_reference_navier_stokes", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        out = {"config": "unmodified reference NavierStokesSimulator.step(), 128x128, K=20 (its literal), 1 sequence"}
+        for name, device, nsteps in (("cpu", "cpu", 10), ("cuda_eager", str(dev), 20)):
+            sim = mod.NavierStokesSimulator((128, 128), 0.01, 0.001, device)
+            sim.add_smoke_source(64, 64, radius=8, intensity=1.5)
+            for _ in range(3):
+                sim.step()
+            if device != "cpu":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(nsteps):
+                sim.step()
+            if device != "cpu":
+                torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out[name] = {"cell_steps_per_s": 128 * 128 * nsteps / dt, "ms_per_step": 1e3 * dt / nsteps,
+                         "threads": torch.get_num_threads() if device == "cpu" else None}
+        return out
+    except Exception as e:           # informational only
+        return {"error": repr(e)[:200]}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -395,6 +429,7 @@ def main():
         "phases_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
     }
     if not args.no_cpu_baseline:
+        out["reference_torch"] = reference_torch_numbers(dev)
         import oracle
         oracle.build()
         cores = os.cpu_count() or 1

@@ -184,6 +184,20 @@ SMK_API int smk_fractal_fields(float* perlin, float* mandel, float* mul, int32_t
 SMK_API int smk_apply_mul(const float* field, const float* mul, float* out, int32_t rows, int32_t cols,
                   int32_t pitch, int32_t batch, int64_t stride, void* stream);
 
+/* SmokeSimulator.get_chaos_features ingredients (smoke_simulator.py:47-140) for nframes frames that are
+ * frame_stride elements apart, each [h][pitch]:
+ *   box_counts[nframes][5]  boxes of side 2,4,8,16,32 holding a pixel above the frame mean       (:89-124)
+ *   hist[nframes][nbins]    torch.histogram(frame, bins=nbins, range=(lo, hi)) counts; edges[nbins+1] is the
+ *                           torch.linspace(lo, hi, nbins+1) the reference's bin search uses       (:126-140)
+ *   mean_out[nframes]       frame mean (may be NULL)
+ * box_counts and hist are overwritten. */
+SMK_API int smk_frame_features(const float* frames, int64_t frame_stride, int32_t nframes, int32_t h, int32_t w,
+                       int32_t pitch, const float* edges, int32_t nbins, float lo, float hi,
+                       int32_t* box_counts, int32_t* hist, float* mean_out, void* stream);
+/*   sumsq[n] = ||frame[n+1] - frame[n]||^2 (double), n < nframes-1: the distances of compute_lyapunov_exponent (:67-87) */
+SMK_API int smk_frame_distances(const float* frames, int64_t frame_stride, int32_t nframes, int32_t h, int32_t w,
+                        int32_t pitch, double* sumsq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,8 @@ SIGNATURES = {
     "smk_run_steps": [GP, SP, PP, c_i32, c_p, c_i64, c_i64, c_p, c_p],
     "smk_div_norms": [GP, c_p, c_p, c_p, c_p],
     "smk_fractal_fields": [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f, c_i32, c_p, c_p, c_p, c_p, c_p],
+    "smk_frame_features": [c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_f, c_f, c_p, c_p, c_p, c_p],
+    "smk_frame_distances": [c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
     "smk_apply_mul": [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i64, c_p],
 }
 

@@ -309,4 +309,25 @@ int smk_apply_mul(const float* field, const float* mul, float* out, int32_t rows
     return launch_apply_mul(field, mul, out, rows, cols, pitch, batch, stride, (cudaStream_t)stream);
 }
 
+int smk_frame_features(const float* frames, int64_t frame_stride, int32_t nframes, int32_t h, int32_t w, int32_t pitch,
+                       const float* edges, int32_t nbins, float lo, float hi, int32_t* box_counts, int32_t* hist,
+                       float* mean_out, void* stream)
+{
+    if (!frames || !edges || !box_counts || !hist) return fail(SMK_EINVAL, "smk_frame_features: NULL pointer");
+    if (nframes < 0 || h < 1 || w < 1 || pitch < w || nbins < 1 || nbins > 8192 || !(hi > lo))
+        return fail(SMK_EINVAL, "smk_frame_features: bad arguments (%d frames of %d x %d pitch %d, %d bins)", nframes, h, w, pitch, nbins);
+    if (nframes > 1 && frame_stride < (int64_t)h * pitch) return fail(SMK_EINVAL, "smk_frame_features: frame_stride smaller than a frame");
+    return launch_frame_features(frames, frame_stride, nframes, h, w, pitch, edges, nbins, lo, hi, box_counts, hist, mean_out,
+                                 (cudaStream_t)stream);
+}
+
+int smk_frame_distances(const float* frames, int64_t frame_stride, int32_t nframes, int32_t h, int32_t w, int32_t pitch,
+                        double* sumsq, void* stream)
+{
+    if (!frames || !sumsq) return fail(SMK_EINVAL, "smk_frame_distances: NULL pointer");
+    if (nframes < 0 || h < 1 || w < 1 || pitch < w) return fail(SMK_EINVAL, "smk_frame_distances: bad arguments");
+    if (nframes > 1 && frame_stride < (int64_t)h * pitch) return fail(SMK_EINVAL, "smk_frame_distances: frame_stride smaller than a frame");
+    return launch_frame_distances(frames, frame_stride, nframes, h, w, pitch, sumsq, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -84,6 +84,9 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
 int launch_div_norms(const smk_grid_t* g, const float* u, const float* v, float* out, cudaStream_t s);
 int launch_fractal_fields(float* perlin, float* mandel, float* mul, int na, int nb, int pitch, float intensity, int iterations,
                           const float* px, const float* py, const float* mx, const float* my, cudaStream_t s);
+int launch_frame_features(const float* frames, int64_t frame_stride, int nframes, int h, int w, int pitch,
+                          const float* edges, int nbins, float lo, float hi, int* box_counts, int* hist, float* mean_out, cudaStream_t s);
+int launch_frame_distances(const float* frames, int64_t frame_stride, int nframes, int h, int w, int pitch, double* sumsq, cudaStream_t s);
 int launch_apply_mul(const float* f, const float* mul, float* out, int rows, int cols, int pitch, int batch, int64_t stride, cudaStream_t s);
 
 }  // namespace smk

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import chaos
 from .fractal_generator import FractalGenerator
 from .navier_stokes import NavierStokesSimulator
 
@@ -86,6 +87,17 @@ class SmokeSimulator(nn.Module):
         return host.permute(1, 0, 2, 3)[..., :L.w]
 
     # -------------------------------------------------------------- chaos features (smoke_simulator.py:47-140)
+    def _staged_history(self, n):
+        """The last n history frames as one contiguous padded [n, h, pitch] device tensor."""
+        ns = self.ns_solver
+        L = ns._layout
+        buf = torch.zeros(n, L.h, L.pitch_c, dtype=torch.float32, device=ns._cuda)
+        for k, f in enumerate(self.history[-n:]):
+            if f.dim() != 2:
+                raise ValueError("chaos features are defined for single simulations (batch == 1), as in the reference")
+            buf[k, :, :L.w] = f.to(ns._cuda)
+        return buf
+
     def get_chaos_features(self):
         if len(self.history) < 10:
             return {}
@@ -99,42 +111,88 @@ class SmokeSimulator(nn.Module):
         """Mean log-growth of the distance between consecutive frames over the last 20 (smoke_simulator.py:67-87)."""
         if len(self.history) < 20:
             return 0.0
-        states = torch.stack(self.history[-20:])
-        diffs = states[1:] - states[:-1]
-        distances = torch.linalg.vector_norm(diffs.reshape(diffs.shape[0], -1), dim=1).cpu().numpy().astype(np.float64)
-        if len(distances) > 1:
-            log_distances = np.log(distances + 1e-8)
-            return max(0, np.mean(np.diff(log_distances)))
-        return 0.0
+        return chaos.lyapunov_from_distances(chaos.frame_distances(self._staged_history(20), self.ns_solver.w))
 
     def compute_fractal_dimension(self):
         """Box-counting dimension of the above-mean mask at scales 2..32 (smoke_simulator.py:89-124)."""
         if not self.history:
             return 0.0
-        current = self.history[-1]
-        binary = current > current.mean()
-        scales = [2, 4, 8, 16, 32]
-        counts = []
-        h, w = binary.shape[-2:]
-        for s in scales:
-            bh, bw = h // s, w // s
-            if bh == 0 or bw == 0:
-                counts.append(0)
-                continue
-            boxes = binary[..., :bh * s, :bw * s].reshape(bh, s, bw, s)
-            counts.append(int(boxes.any(dim=3).any(dim=1).sum().item()))
-        log_scales = np.log(scales)
-        log_counts = np.log(np.array(counts) + 1)
-        return abs(np.polyfit(log_scales, log_counts, 1)[0])
+        box, _ = chaos.frame_counts(self._staged_history(1), self.ns_solver.w)
+        return chaos.fractal_dimension_from_counts(box[0].cpu().numpy())
 
     def compute_entropy(self):
         """Shannon entropy of the 256-bin histogram of the last frame over [0, 1] (smoke_simulator.py:126-140)."""
         if not self.history:
             return 0.0
-        cur = self.history[-1].detach().cpu()
-        hist = torch.histogram(cur.flatten(), bins=256, range=(0, 1))
-        probs = hist.hist.float() / hist.hist.sum()
-        return (-torch.sum(probs * torch.log2(probs + 1e-8))).item()
+        _, hist = chaos.frame_counts(self._staged_history(1), self.ns_solver.w)
+        return chaos.entropy_from_hist(hist[0])
+
+    # -------------------------------------------------------------- dataset back-end (data_loader.py:37-99)
+    def generate_dataset(self, num_samples, sequence_length=20, rng=None, to_cpu=False, progress=None):
+        """Batched replacement of SyntheticSmokeDataset._generate_synthetic_data (data_loader.py:37-99).
+
+        Draws the emitters of sample after sample with the same np.random call sequence as the reference
+        (count in [1,3], then x, y, intensity per emitter, :49-58; `rng` defaults to the global np.random so a
+        seeded run draws what the reference draws), simulates `batch` samples at a time, evaluates the chaos
+        features of every frame t >= 10 on the device and averages them per sample (:71-88).  The history
+        the reference never clears between samples (its Lyapunov feature of sample k sees the tail of sample
+        k-1) is reproduced: distances run over the frames in sample-major order.
+        Returns the reference's list of dicts: 'sequence' [T, h, w], 'chaos_features', 'source_config'."""
+        rng = np.random if rng is None else rng
+        ns = self.ns_solver
+        L = ns._layout
+        B, T, h, w = ns.batch, int(sequence_length), ns.h, ns.w
+        if self.history:
+            raise RuntimeError("generate_dataset starts from an empty history, like a freshly built reference simulator")
+        fmul = self.fractal_gen.multiplier((h, w), 0.05)
+        data, prev_last, all_dist = [], None, []          # all_dist[m] = ||frame m+1 - frame m|| over the flat sample-major order
+        keep_cuda = ns._out_device.type == "cuda" and not to_cpu
+        for first in range(0, num_samples, B):
+            nb = min(B, num_samples - first)
+            configs = []
+            for _ in range(nb):
+                n_src = rng.randint(1, 4)
+                pos, inten = [], []
+                for _ in range(n_src):
+                    x = rng.randint(20, w - 20)
+                    y = rng.randint(20, h - 20)
+                    intensity = rng.uniform(0.5, 2.0)
+                    pos.append((x, y))
+                    inten.append(intensity)
+                configs.append((pos, inten))
+            ns.setup_grid()
+            ns.add_sources([[(x, y, 8, i) for (x, y), i in zip(p, q)] for p, q in configs] + [[] for _ in range(B - nb)])
+            padded = torch.empty(B, T, h, L.pitch_c, dtype=torch.float32, device=ns._cuda)
+            ns.run_steps(T, fmul=fmul, out=padded)
+            flat = padded.view(B * T, h, L.pitch_c)[: nb * T]
+            box, hist = chaos.frame_counts(flat, w)
+            if prev_last is not None:                                              # seam with the previous chunk
+                all_dist.extend(chaos.frame_distances(torch.stack([prev_last, flat[0]]), w))
+            all_dist.extend(chaos.frame_distances(flat, w))
+            prev_last = flat[-1].clone()
+            box_h, hist_h = box.cpu().numpy(), hist.cpu()
+            seqs = padded[:nb, :, :, :w]
+            seqs = seqs.contiguous() if keep_cuda else seqs.cpu()
+            for s in range(nb):
+                feats = []
+                for t in range(10, T):                                             # data_loader.py:71 "wait for stabilization"
+                    n = (first + s) * T + t                                        # flat index; the history holds frames <= n
+                    lyap = chaos.lyapunov_from_distances(all_dist[n - 19: n]) if n + 1 >= 20 else 0.0
+                    feats.append((lyap, chaos.fractal_dimension_from_counts(box_h[s * T + t]),
+                                  chaos.entropy_from_hist(hist_h[s * T + t])))
+                if feats:
+                    avg = {"lyapunov_exponent": np.mean([f[0] for f in feats]), "fractal_dimension": np.mean([f[1] for f in feats]),
+                           "entropy": np.mean([f[2] for f in feats])}
+                else:
+                    avg = {"lyapunov_exponent": 0.0, "fractal_dimension": 1.0, "entropy": 0.0}
+                data.append({"sequence": seqs[s], "chaos_features": avg,
+                             "source_config": {"positions": configs[s][0], "intensities": configs[s][1]}})
+            if progress is not None:
+                progress(nb)
+        # leave the history as the reference's loop would: the last (up to) max_history frames
+        frames = [d["sequence"][t] for d in data[-(self.max_history // max(T, 1) + 2):] for t in range(T)]
+        self.history = frames[-self.max_history:]
+        return data
 
     def forward(self, add_fractal=True):
         return self.simulate_step(add_fractal)
