@@ -50,8 +50,9 @@ WORKLOADS = {
 }
 
 # algorithmic bytes per cell per launch of each kernel family (fp32, each array touched once)
-def phase_bytes_per_cell(K, sweeps_in_launch):
+def phase_bytes_per_cell(K, sweeps_in_launch, steps_in_launch=1):
     return {
+        "step_fused": (100 + 12 * K) * steps_in_launch,   # k_step_fused: whole steps, every phase of SURVEY s8d
         "forces_diffuse_div": 24 + 12,      # R(u,v,d) W(u,v,d)  +  divergence R(u,v) W(div), fused in one kernel
         "jacobi": 12 * sweeps_in_launch,    # per sweep R(p,div) W(p)
         "project": 20,                      # R(p,u,v) W(u,v)
@@ -250,6 +251,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweeps-per-launch", type=int, default=0)
+    ap.add_argument("--step-kernel", default="auto", choices=["auto", "phases", "fused"],
+                    help="auto: whole simulation on one SM for grids <= 128x128 (k_step_fused), else one kernel per phase")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -286,7 +289,8 @@ def main():
     h, w, B, K, T = wl["h"], wl["w"], wl["batch"], wl["K"], wl["tsteps"]
     slab_mode = args.workload == "c4"
     if not slab_mode:
-        sim = SmokeSimulator((h, w), 0.01, 0.001, dev, jacobi_iters=K, batch=B, sweeps_per_launch=args.sweeps_per_launch)
+        sim = SmokeSimulator((h, w), 0.01, 0.001, dev, jacobi_iters=K, batch=B, sweeps_per_launch=args.sweeps_per_launch,
+                             step_kernel=args.step_kernel)
         ns = sim.ns_solver
         L = ns._layout
         ems = [emitters_for_sequence(rank * B + s, h, w) for s in range(B)]
@@ -397,18 +401,29 @@ def main():
     dom_ms, dom_n = prof[dom]
     total_prof_ms = sum(v[0] for v in prof.values())
     sweeps_in_launch = K * T * args.steps / dom_n if dom == "jacobi" else 0
-    bpc = phase_bytes_per_cell(K, sweeps_in_launch)
+    steps_in_launch = T * args.steps / dom_n if dom == "step_fused" else 1
+    bpc = phase_bytes_per_cell(K, sweeps_in_launch, steps_in_launch)
     alg_bytes_per_launch = bpc[dom] * cells_per_launch
     achieved = alg_bytes_per_launch / (dom_ms / dom_n * 1e-3) / 1e9
     kernel_name = {"jacobi": "k_jacobi", "forces_diffuse_div": "k_forces_diffuse_div", "project": "k_project",
-                   "advect_u": "k_advect", "advect_v": "k_advect", "advect_d": "k_advect", "splat": "k_splat"}.get(dom, dom)
+                   "advect_u": "k_advect", "advect_v": "k_advect", "advect_d": "k_advect", "splat": "k_splat",
+                   "step_fused": "k_step_fused"}.get(dom, dom)
+    if dom == "jacobi":
+        note = ("achieved > peak is possible: %d sweeps are fused per launch with the pressure tile on-chip, so real DRAM "
+                "traffic is below the algorithmic 12 B/cell-sweep (see `traffic`)" % round(sweeps_in_launch))
+    elif dom == "step_fused":
+        note = ("achieved > peak is possible: %d whole steps run per launch with u, v, density in shared memory and the pressure "
+                "in registers, so real DRAM traffic is one state read + write per launch and 4 B/cell-step of frames, far below "
+                "the algorithmic %d B/cell-step (see `traffic`); the kernel is bound by FP32 issue, not HBM"
+                % (round(steps_in_launch), 100 + 12 * K))
+    else:
+        note = ""
     roofline = {
         "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": committed_traffic(kernel_name, args.workload), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": dom_ms / dom_n,
         "launches_timed": dom_n, "share_of_step": dom_ms / total_prof_ms,
-        "note": "achieved > peak is possible: %d sweeps are fused per launch with the pressure tile on-chip, so real DRAM "
-                "traffic is below the algorithmic 12 B/cell-sweep (see `traffic`)" % round(sweeps_in_launch) if dom == "jacobi" else "",
+        "note": note,
     }
     step_bytes = 100 + 12 * K
     out = {
@@ -416,7 +431,7 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "grid": [h, w], "sequences_per_gpu": B, "jacobi_iters": K, "time_steps_per_bench_step": T,
-                   "parallelism": parallelism,
+                   "parallelism": parallelism, "step_kernel": ("fused" if (not slab_mode and ns.step_is_fused()) else "phases"),
                    "l2": "no flush: working set %.0f MB per GPU (fields + frames) > 126 MB L2" % (working_set / 1e6)},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

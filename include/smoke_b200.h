@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMK_ABI_VERSION 2
+#define SMK_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SMK_API __attribute__((visibility("default")))
@@ -91,7 +91,16 @@ typedef struct smk_params {
     float dt, c_uv, c_d, decay;
     int32_t jacobi_iters;       /* 20 in the reference (navier_stokes.py:139)                      */
     int32_t sweeps_per_launch;  /* temporal-blocking depth T; 0 = library default                  */
+    int32_t step_kernel;        /* smk_step / smk_run_steps: SMK_STEP_AUTO, _PHASES or _FUSED      */
 } smk_params_t;
+
+/* How smk_step / smk_run_steps execute a step.  Results are bit-identical either way.
+ *   SMK_STEP_PHASES  one kernel per phase (any grid size)
+ *   SMK_STEP_FUSED   the whole simulation on one SM -- u, v, density in shared memory, pressure in registers --
+ *                    for all the steps of the call in a single launch; grids of at most 128 x 128 cells only
+ *                    (SMK_EUNSUPPORTED otherwise)
+ *   SMK_STEP_AUTO    fused when the grid qualifies, else phases                                   */
+enum { SMK_STEP_AUTO = 0, SMK_STEP_PHASES = 1, SMK_STEP_FUSED = 2 };
 
 SMK_API int smk_version(void);
 SMK_API const char* smk_last_error_string(void);
@@ -108,7 +117,7 @@ SMK_API int smk_set_device(int32_t device);
  * profile.  Process-wide, not re-entrant; off by default (no events, no overhead). */
 enum {
     SMK_PH_SPLAT = 0, SMK_PH_FORCES_DIFFUSE_DIV, SMK_PH_JACOBI, SMK_PH_PROJECT,
-    SMK_PH_ADVECT_U, SMK_PH_ADVECT_V, SMK_PH_ADVECT_D, SMK_PH_OTHER, SMK_PH_COUNT
+    SMK_PH_ADVECT_U, SMK_PH_ADVECT_V, SMK_PH_ADVECT_D, SMK_PH_OTHER, SMK_PH_STEP_FUSED, SMK_PH_COUNT
 };
 SMK_API int smk_profile_begin(int32_t max_records);
 SMK_API int smk_profile_end(double* ms_per_phase_host, int64_t* launches_per_phase_host, int32_t nphases);
@@ -165,6 +174,8 @@ SMK_API int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* p
 SMK_API int smk_run_steps(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, int32_t nsteps,
                   float* frames, int64_t frame_step_stride, int64_t frame_batch_stride,
                   const float* fmul, void* stream);
+/*     1 when smk_step / smk_run_steps would take the fused single-launch path for this grid and params */
+SMK_API int smk_step_is_fused(const smk_grid_t* g, const smk_params_t* prm, int32_t* fused_host);
 
 /* diagnostics: per simulation {max|div|, sum div^2} of the un-normalised divergence of (u, v);
  *     out[2*batch] must be zeroed by the caller; warp-shuffle + atomic reduction. */

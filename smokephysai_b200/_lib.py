@@ -34,7 +34,10 @@ class State(C.Structure):                    # smk_state_t
 
 class Params(C.Structure):                   # smk_params_t
     _fields_ = [("dt", c_f), ("c_uv", c_f), ("c_d", c_f), ("decay", c_f),
-                ("jacobi_iters", c_i32), ("sweeps_per_launch", c_i32)]
+                ("jacobi_iters", c_i32), ("sweeps_per_launch", c_i32), ("step_kernel", c_i32)]
+
+
+STEP_KERNELS = {"auto": 0, "phases": 1, "fused": 2}           # SMK_STEP_AUTO / _PHASES / _FUSED
 
 
 GP, SP, PP = C.POINTER(Grid), C.POINTER(State), C.POINTER(Params)
@@ -59,6 +62,7 @@ SIGNATURES = {
     "smk_advect_slab": [GP, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_f, c_f, C.POINTER(SlabCheck), c_p],
     "smk_step": [GP, SP, PP, c_p, c_i64, c_p, c_p],
     "smk_run_steps": [GP, SP, PP, c_i32, c_p, c_i64, c_i64, c_p, c_p],
+    "smk_step_is_fused": [GP, PP, C.POINTER(c_i32)],
     "smk_div_norms": [GP, c_p, c_p, c_p, c_p],
     "smk_fractal_fields": [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f, c_i32, c_p, c_p, c_p, c_p, c_p],
     "smk_frame_features": [c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_f, c_f, c_p, c_p, c_p, c_p],
@@ -110,7 +114,7 @@ def launch_count():
     return n.value
 
 
-PHASES = ("splat", "forces_diffuse_div", "jacobi", "project", "advect_u", "advect_v", "advect_d", "other")
+PHASES = ("splat", "forces_diffuse_div", "jacobi", "project", "advect_u", "advect_v", "advect_d", "other", "step_fused")
 
 
 def profile_begin(max_records=4096):

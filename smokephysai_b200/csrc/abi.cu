@@ -247,6 +247,28 @@ int smk_advect_slab(const smk_grid_t* g, const float* field, float* out, int32_t
     return launch_advect(g, field, out, rows, cols, pitch, 0, u, v, dt, scale, nullptr, 0, nullptr, chk, (cudaStream_t)stream);
 }
 
+static int pick_step_kernel(const smk_grid_t* g, const smk_params_t* prm, int* fused)
+{
+    *fused = 0;
+    if (prm->step_kernel == SMK_STEP_PHASES) return SMK_OK;
+    if (prm->step_kernel != SMK_STEP_AUTO && prm->step_kernel != SMK_STEP_FUSED)
+        return fail(SMK_EINVAL, "smk_step: step_kernel %d is not SMK_STEP_AUTO/_PHASES/_FUSED", prm->step_kernel);
+    if (fused_supported(g)) { *fused = 1; return SMK_OK; }
+    if (prm->step_kernel == SMK_STEP_FUSED)
+        return fail(SMK_EUNSUPPORTED, "smk_step: SMK_STEP_FUSED needs a non-slab grid of at most 128 x 128 cells, got %d x %d", g->h, g->w);
+    return SMK_OK;
+}
+
+int smk_step_is_fused(const smk_grid_t* g, const smk_params_t* prm, int32_t* fused_host)
+{
+    SMK_TRY(check_grid(g, "smk_step_is_fused"));
+    if (!prm || !fused_host) return fail(SMK_EINVAL, "smk_step_is_fused: NULL");
+    int f = 0;
+    SMK_TRY(pick_step_kernel(g, prm, &f));
+    *fused_host = f;
+    return SMK_OK;
+}
+
 int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, float* frame, int64_t frame_stride,
              const float* fmul, void* stream)
 {
@@ -259,6 +281,11 @@ int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, floa
     if (prm->jacobi_iters < 0) return fail(SMK_EINVAL, "smk_step: negative jacobi_iters");
     if (!(prm->dt != 0.0f)) return fail(SMK_EINVAL, "smk_step: dt must be non-zero");
     cudaStream_t s = (cudaStream_t)stream;
+    int fused = 0;
+    SMK_TRY(pick_step_kernel(g, prm, &fused));
+    if (fused)
+        return launch_steps_fused(g, st->u[st->cur_u], st->v[st->cur_v], st->d[st->cur_d], st->p[st->cur_p], 1, frame, 0, frame_stride,
+                                  fmul, prm->dt, prm->c_uv, prm->c_d, prm->decay, prm->jacobi_iters, s);
     const int cu = st->cur_u, cv = st->cur_v, cd = st->cur_d;
     float *u0 = st->u[cu], *u1 = st->u[cu ^ 1], *v0 = st->v[cv], *v1 = st->v[cv ^ 1], *d0 = st->d[cd], *d1 = st->d[cd ^ 1];
     // 1-2. buoyancy + diffusion + divergence                                   navier_stokes.py:154-160, :136
@@ -279,6 +306,21 @@ int smk_run_steps(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
                   float* frames, int64_t frame_step_stride, int64_t frame_batch_stride, const float* fmul, void* stream)
 {
     if (nsteps < 0) return fail(SMK_EINVAL, "smk_run_steps: negative nsteps");
+    if (nsteps > 1 && g && st && prm) {
+        // the fused kernel keeps the state on chip across all the steps of the call: one launch
+        SMK_TRY(check_grid(g, "smk_run_steps"));
+        int fused = 0;
+        SMK_TRY(pick_step_kernel(g, prm, &fused));
+        if (fused) {
+            SMK_TRY(check_ptrs("smk_run_steps", {st->u[0], st->u[1], st->v[0], st->v[1], st->d[0], st->d[1], st->p[0], st->p[1]}));
+            if ((st->cur_u | st->cur_v | st->cur_d | st->cur_p) & ~1) return fail(SMK_EINVAL, "smk_run_steps: cur_* must be 0 or 1");
+            if (prm->jacobi_iters < 0) return fail(SMK_EINVAL, "smk_run_steps: negative jacobi_iters");
+            if (!(prm->dt != 0.0f)) return fail(SMK_EINVAL, "smk_run_steps: dt must be non-zero");
+            return launch_steps_fused(g, st->u[st->cur_u], st->v[st->cur_v], st->d[st->cur_d], st->p[st->cur_p], nsteps, frames,
+                                      frame_step_stride, frame_batch_stride, fmul, prm->dt, prm->c_uv, prm->c_d, prm->decay,
+                                      prm->jacobi_iters, (cudaStream_t)stream);
+        }
+    }
     for (int t = 0; t < nsteps; ++t)
         SMK_TRY(smk_step(g, st, prm, frames ? frames + (int64_t)t * frame_step_stride : nullptr, frame_batch_stride, fmul, stream));
     return SMK_OK;

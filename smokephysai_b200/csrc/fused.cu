@@ -1,0 +1,451 @@
+// fused.cu -- n whole step()s (navier_stokes.py:151-173) of a simulation that fits on one SM, in ONE kernel.
+//
+// For grids up to 128 x 128 (the reference's config.yaml default, and BASELINE config 2: hundreds of independent
+// 128 x 128 sequences) the entire state of a simulation fits on chip: u, v and density live in shared memory
+// (66,048 + 67,584 + 65,536 B), the pressure and the divergence in registers (the 128 x 128 register tile of
+// k_jacobi: a warp owns 8 rows, a lane 4 columns).  A CTA of 16 warps owns one simulation and runs every phase
+// of every step on it -- buoyancy, the three diffusions, divergence, K Jacobi sweeps, gradient subtract, the three
+// sequential advections, decay, the returned (fractal-scaled) frame -- touching HBM only to read the state once
+// per launch, write one frame per step and write the state back at the end: 4 B per cell-step (+ 36 B per cell
+// per launch) instead of the ~104 B per cell-step of the phase-per-kernel path, and one launch instead of 6 n.
+//
+// Two thread -> cell mappings are used, both over the warp's 8 rows:
+//   strip  : lane l owns columns 4l .. 4l+3 (one LDS.128 / STS.128 per row, neighbours by shuffle) -- buoyancy,
+//            diffusion, divergence, Jacobi, gradient subtract, frame output;
+//   cyclic : lane l owns columns l, l+32, l+64, l+96 -- advection, whose back-traced gathers then hit 32 distinct
+//            banks for sub-cell displacements (the strip mapping would be a 4-way conflict on every gather).
+// Out-of-place phases (diffusion, advection) are made in-place-safe through registers: every thread computes
+// the new values of its cells, the CTA synchronises, then everyone writes back.  u's staggered row 128 and v's
+// staggered column 128 (present when h == 128 / w == 128) are spread over lanes 0..7 of every warp.
+// Arithmetic is the same rounded-once sequence as the tiled kernels, so results are bit-identical to them.
+#include "common.cuh"
+#include "jacobi_core.cuh"
+
+namespace smk {
+
+constexpr int FZ_R = 8, FZ_NW = 16, FZ_THREADS = FZ_NW * 32;
+constexpr int FZ_PU = 128, FZ_PV = 132, FZ_PD = 128;                 // shared-memory row pitches
+constexpr int FZ_SU = 129 * FZ_PU, FZ_SV = 128 * FZ_PV, FZ_SD = 128 * FZ_PD;     // floats
+constexpr size_t FZ_SMEM = (size_t)(FZ_SU + FZ_SV + FZ_SD) * 4 + sizeof(float4) * 2 * 2 * FZ_NW * 32;
+
+struct FusedArgs {
+    float* U; float* V; float* D; float* P;              // live state, updated in place
+    float* frames; const float* fmul;                     // frames may be NULL; fmul may be NULL
+    int h, w, pu, pv, pc;
+    long long su_, sv_, sc_, frame_step_stride, frame_batch_stride;
+    float dt, c_uv, c_d, decay;
+    int K, nsteps;
+};
+
+__device__ __forceinline__ float4 zlds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void zsts4(float* p, const float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// diffusion_step at one cell: f + c*((((up+down)+left)+right) - 4f)                    navier_stokes.py:69-72
+__device__ __forceinline__ float zdiff1(float f, float up, float dn, float l, float r, float c)
+{
+    float s = up + dn;
+    s = s + l;
+    s = s + r;
+    return f + c * (s - 4.0f * f);
+}
+// ... with replicate padding by index clamp (:57-66), any cell of a rows x cols field in shared memory
+__device__ __forceinline__ float zdiff_cell(const float* F, int pitch, int rows, int cols, int i, int j, float c)
+{
+    const int iu = max(i - 1, 0), id = min(i + 1, rows - 1), jl = max(j - 1, 0), jr = min(j + 1, cols - 1);
+    return zdiff1(F[i * pitch + j], F[iu * pitch + j], F[id * pitch + j], F[i * pitch + jl], F[i * pitch + jr], c);
+}
+
+// Strip-mapped diffusion of the thread's 8 x 4 cells of a field whose rows [0, 128) x cols [0, 128) part is full
+// (ROWS, COLS in {128, 129}).  Rows slide through registers; the left / right neighbours of the strip come from
+// the adjacent lanes, replicate padding at the field's edge.
+template <int ROWS, int COLS, int PITCH>
+__device__ __forceinline__ void zdiffuse_strip_full(const float* F, const float c, float4 (&out)[FZ_R], const int r0, const int c0, const int lane)
+{
+    float4 up = zlds4(F + max(r0 - 1, 0) * PITCH + c0);
+    float4 cur = zlds4(F + r0 * PITCH + c0);
+#pragma unroll
+    for (int r = 0; r < FZ_R; ++r) {
+        const int i = r0 + r;
+        const float4 dn = zlds4(F + min(i + 1, ROWS - 1) * PITCH + c0);
+        float left = __shfl_up_sync(0xffffffffu, cur.w, 1);
+        float right = __shfl_down_sync(0xffffffffu, cur.x, 1);
+        if (lane == 0) left = cur.x;
+        if (lane == 31) right = (COLS > 128) ? F[i * PITCH + 128] : cur.w;
+        out[r].x = zdiff1(cur.x, up.x, dn.x, left, cur.y, c);
+        out[r].y = zdiff1(cur.y, up.y, dn.y, cur.x, cur.z, c);
+        out[r].z = zdiff1(cur.z, up.z, dn.z, cur.y, cur.w, c);
+        out[r].w = zdiff1(cur.w, up.w, dn.w, cur.z, right, c);
+        up = cur; cur = dn;
+    }
+}
+
+// advection_step at one cell (navier_stokes.py:74-131): same restatement as k_advect (stencil.cu) with the
+// field, u and v in shared memory.  rows x cols is the advected field, h x w the cell grid.
+template <int PITCH>
+__device__ __forceinline__ float zadvect_cell(const float* F, const int rows, const int cols, const float* su, const float* sv,
+                                              const int h, const int w, const int i, const int j, const float dt)
+{
+    // a9: u_i = 0.5*U[i][j] + 0.5*U[i][j+1] for j <= w-2 and i <= h-1, else 0;  v_i likewise along rows
+    float ui = 0.0f, vi = 0.0f;
+    if (j <= w - 2 && i <= h - 1) ui = 0.5f * su[i * FZ_PU + j] + 0.5f * su[i * FZ_PU + j + 1];
+    if (i <= h - 2 && j <= w - 1) vi = 0.5f * sv[i * FZ_PV + j] + 0.5f * sv[(i + 1) * FZ_PV + j];
+    const float xmax = (float)(cols - 1), ymax = (float)(rows - 1);
+    float px = (float)j - dt * ui;
+    float py = (float)i - dt * vi;
+    px = fminf(fmaxf(px, 0.0f), xmax);
+    py = fminf(fmaxf(py, 0.0f), ymax);
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const float fx1 = fminf(fx0 + 1.0f, xmax), fy1 = fminf(fy0 + 1.0f, ymax);
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    const int dx = (fx1 != fx0) ? 1 : 0, dy = (fy1 != fy0) ? PITCH : 0;
+    const float ax = fx1 - px, bx = px - fx0, ay = fy1 - py, by = py - fy0;
+    const float* q = F + (y0 * PITCH + x0);
+    float s = (ax * ay) * q[0] + (bx * ay) * q[dx];
+    s = s + (ax * by) * q[dy];
+    s = s + (bx * by) * q[dy + dx];
+    return s;
+}
+
+// FULL: h == w == 128 (every strip cell is a grid cell and the staggered extras exist); otherwise any h, w <= 128.
+template <bool FULL>
+__global__ void __launch_bounds__(FZ_THREADS, 1)
+k_step_fused(const FusedArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    float* su = smem;
+    float* sv = su + FZ_SU;
+    float* sd = sv + FZ_SV;
+    float4 (*halo)[2][FZ_NW][32] = reinterpret_cast<float4 (*)[2][FZ_NW][32]>(sd + FZ_SD);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h = FULL ? 128 : a.h, w = FULL ? 128 : a.w;
+    const int pu = FULL ? 128 : a.pu, pv = FULL ? 132 : a.pv, pc = FULL ? 128 : a.pc;
+    const size_t b = blockIdx.x;
+    float* __restrict__ gU = a.U + b * a.su_;
+    float* __restrict__ gV = a.V + b * a.sv_;
+    float* __restrict__ gD = a.D + b * a.sc_;
+    float* __restrict__ gP = a.P + b * a.sc_;
+    const int r0 = warp * FZ_R, c0 = lane * 4;
+    // the staggered extras: u[128][xe] and v[xe][128], xe = 8*warp + lane for lanes 0..7
+    const int xe = 8 * warp + lane;
+    const bool xu = (h == 128) && lane < 8 && xe < w;
+    const bool xv = (w == 128) && lane < 8 && xe < h;
+    const float dt = a.dt;
+
+    // ---- load the state: u, v, density to shared memory, pressure to registers ---------------------------
+    if (!FULL) {
+        for (int k = tid; k < (int)(FZ_SU + FZ_SV + FZ_SD) / 4; k += FZ_THREADS) zsts4(smem + 4 * k, make_float4(0.f, 0.f, 0.f, 0.f));
+        __syncthreads();
+    }
+    {
+        const int gu4 = pu >> 2, gv4 = pv >> 2, gc4 = pc >> 2;
+        for (int k = tid; k < (h + 1) * gu4; k += FZ_THREADS) {
+            const int i = k / gu4, g = k - i * gu4;
+            zsts4(su + i * FZ_PU + 4 * g, *reinterpret_cast<const float4*>(gU + (size_t)i * pu + 4 * g));
+        }
+        for (int k = tid; k < h * gv4; k += FZ_THREADS) {
+            const int i = k / gv4, g = k - i * gv4;
+            zsts4(sv + i * FZ_PV + 4 * g, *reinterpret_cast<const float4*>(gV + (size_t)i * pv + 4 * g));
+        }
+        for (int k = tid; k < h * gc4; k += FZ_THREADS) {
+            const int i = k / gc4, g = k - i * gc4;
+            zsts4(sd + i * FZ_PD + 4 * g, *reinterpret_cast<const float4*>(gD + (size_t)i * pc + 4 * g));
+        }
+    }
+    float4 P[FZ_R];
+    const bool colin = c0 < pc;
+#pragma unroll
+    for (int r = 0; r < FZ_R; ++r) {
+        const int i = r0 + r;
+        P[r] = (colin && i < h) ? *reinterpret_cast<const float4*>(gP + (size_t)i * pc + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float cm0 = (c0 + 0 >= 1 && c0 + 0 <= w - 2) ? 0.25f : 0.f;
+    const float cm1 = (c0 + 1 >= 1 && c0 + 1 <= w - 2) ? 0.25f : 0.f;
+    const float cm2 = (c0 + 2 >= 1 && c0 + 2 <= w - 2) ? 0.25f : 0.f;
+    const float cm3 = (c0 + 3 >= 1 && c0 + 3 <= w - 2) ? 0.25f : 0.f;
+    const bool fast = (r0 >= 1) && (r0 + FZ_R - 1 <= h - 2);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+
+    // frame output of the step just finished (:173, fractal_generator.py:62) and buoyancy of the next one
+    // (:154-155: v[:, :-1] += dt * (density * 0.1)); both read the thread's own strip of density.
+    auto frame_and_buoyancy = [&](float* frame, const bool buoy) {
+#pragma unroll
+        for (int r = 0; r < FZ_R; ++r) {
+            const int i = r0 + r;
+            if (FULL || (i < h && colin)) {
+                const float4 d4 = zlds4(sd + i * FZ_PD + c0);
+                if (frame) {
+                    float4 fr = d4;
+                    if (a.fmul) {
+                        const float4 m = __ldg(reinterpret_cast<const float4*>(a.fmul + (size_t)i * pc + c0));
+                        fr.x = fr.x + m.x * fr.x; fr.y = fr.y + m.y * fr.y; fr.z = fr.z + m.z * fr.z; fr.w = fr.w + m.w * fr.w;
+                    }
+                    *reinterpret_cast<float4*>(frame + (size_t)i * pc + c0) = fr;
+                }
+                if (buoy) {
+                    float4 v4 = zlds4(sv + i * FZ_PV + c0);
+                    if (FULL || c0 + 0 < w) v4.x = v4.x + dt * (d4.x * 0.1f);
+                    if (FULL || c0 + 1 < w) v4.y = v4.y + dt * (d4.y * 0.1f);
+                    if (FULL || c0 + 2 < w) v4.z = v4.z + dt * (d4.z * 0.1f);
+                    if (FULL || c0 + 3 < w) v4.w = v4.w + dt * (d4.w * 0.1f);
+                    zsts4(sv + i * FZ_PV + c0, v4);
+                }
+            }
+        }
+    };
+
+    if (a.nsteps > 0) frame_and_buoyancy(nullptr, true);
+    __syncthreads();
+
+    for (int t = 0; t < a.nsteps; ++t) {
+        // ---- a4 diffusion of u (rows 0..h), v (cols 0..w), density                    navier_stokes.py:158-160
+        {
+            float4 R[FZ_R];
+            float X = 0.f;
+            // u
+            if (FULL) zdiffuse_strip_full<129, 128, FZ_PU>(su, a.c_uv, R, r0, c0, lane);
+            else {
+#pragma unroll
+                for (int r = 0; r < FZ_R; ++r) {
+                    const int i = r0 + r;
+                    float o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o[k] = (i <= h && c0 + k < w) ? zdiff_cell(su, FZ_PU, h + 1, w, i, c0 + k, a.c_uv) : 0.f;
+                    R[r] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            if (xu) X = zdiff_cell(su, FZ_PU, h + 1, w, 128, xe, a.c_uv);
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r) { const int i = r0 + r; if (FULL || (i <= h && colin)) zsts4(su + i * FZ_PU + c0, R[r]); }
+            if (xu) su[128 * FZ_PU + xe] = X;
+            // v (reads sv only: no barrier needed after the u write-back)
+            if (FULL) zdiffuse_strip_full<128, 129, FZ_PV>(sv, a.c_uv, R, r0, c0, lane);
+            else {
+#pragma unroll
+                for (int r = 0; r < FZ_R; ++r) {
+                    const int i = r0 + r;
+                    float o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o[k] = (i < h && c0 + k <= w) ? zdiff_cell(sv, FZ_PV, h, w + 1, i, c0 + k, a.c_uv) : 0.f;
+                    R[r] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            if (xv) X = zdiff_cell(sv, FZ_PV, h, w + 1, xe, 128, a.c_uv);
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r) { const int i = r0 + r; if (FULL || (i < h && c0 <= w)) zsts4(sv + i * FZ_PV + c0, R[r]); }
+            if (xv) sv[xe * FZ_PV + 128] = X;
+            // density
+            if (FULL) zdiffuse_strip_full<128, 128, FZ_PD>(sd, a.c_d, R, r0, c0, lane);
+            else {
+#pragma unroll
+                for (int r = 0; r < FZ_R; ++r) {
+                    const int i = r0 + r;
+                    float o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o[k] = (i < h && c0 + k < w) ? zdiff_cell(sd, FZ_PD, h, w, i, c0 + k, a.c_d) : 0.f;
+                    R[r] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r) { const int i = r0 + r; if (FULL || (i < h && colin)) zsts4(sd + i * FZ_PD + c0, R[r]); }
+            __syncthreads();
+        }
+
+        // ---- a5 divergence into registers: (((u[i+1][j] - u[i][j]) + v[i][j+1]) - v[i][j]) / dt           :136
+        float4 Dv[FZ_R];
+        {
+            float4 ua = zlds4(su + r0 * FZ_PU + c0);
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r) {
+                const int i = r0 + r;
+                const float4 ub = zlds4(su + (i + 1) * FZ_PU + c0);
+                const float4 va = zlds4(sv + i * FZ_PV + c0);
+                const float vr = sv[i * FZ_PV + c0 + 4];
+                float4 o;
+                o.x = (((ub.x - ua.x) + va.y) - va.x) / dt;
+                o.y = (((ub.y - ua.y) + va.z) - va.y) / dt;
+                o.z = (((ub.z - ua.z) + va.w) - va.z) / dt;
+                o.w = (((ub.w - ua.w) + vr) - va.w) / dt;
+                if (!FULL) {
+                    if (i >= h) o = zero4;
+                    if (c0 + 0 >= w) o.x = 0.f;
+                    if (c0 + 1 >= w) o.y = 0.f;
+                    if (c0 + 2 >= w) o.z = 0.f;
+                    if (c0 + 3 >= w) o.w = 0.f;
+                }
+                Dv[r] = o;
+                ua = ub;
+            }
+        }
+
+        // ---- a6 K Jacobi sweeps on the register tile (see jacobi.cu)                                  :139-145
+        halo[0][0][warp][lane] = P[0];
+        halo[0][1][warp][lane] = P[FZ_R - 1];
+        __syncthreads();
+        for (int s = 0; s < a.K; ++s) {
+            const int buf = s & 1;
+            const float4 up = warp > 0 ? halo[buf][1][warp - 1][lane] : zero4;
+            const float4 dn = warp < FZ_NW - 1 ? halo[buf][0][warp + 1][lane] : zero4;
+            float4* pf = &halo[buf ^ 1][0][warp][lane];
+            float4* pl = &halo[buf ^ 1][1][warp][lane];
+            if (fast) sweep_rows<FZ_R, true>(P, Dv, up, dn, cm0, cm1, cm2, cm3, r0, h, pf, pl);
+            else      sweep_rows<FZ_R, false>(P, Dv, up, dn, cm0, cm1, cm2, cm3, r0, h, pf, pl);
+            __syncthreads();
+        }
+
+        // ---- a7 gradient subtract, in place on the thread's strip                                     :148-149
+        {
+            // halo[K & 1][1][warp - 1] holds the final last row of the warp above: the "row above" of row r0
+            float4 pabove = warp > 0 ? halo[a.K & 1][1][warp - 1][lane] : zero4;
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r) {
+                const int i = r0 + r;
+                const float4 pc4 = P[r];
+                const float pleft = __shfl_up_sync(0xffffffffu, pc4.w, 1);
+                if (FULL || (i < h && colin)) {
+                    float4 u4 = zlds4(su + i * FZ_PU + c0);
+                    float4 v4 = zlds4(sv + i * FZ_PV + c0);
+                    if (i >= 1) {
+                        if (FULL || c0 + 0 < w) u4.x = u4.x - dt * (pc4.x - pabove.x);
+                        if (FULL || c0 + 1 < w) u4.y = u4.y - dt * (pc4.y - pabove.y);
+                        if (FULL || c0 + 2 < w) u4.z = u4.z - dt * (pc4.z - pabove.z);
+                        if (FULL || c0 + 3 < w) u4.w = u4.w - dt * (pc4.w - pabove.w);
+                        zsts4(su + i * FZ_PU + c0, u4);
+                    }
+                    if (c0 >= 1) v4.x = v4.x - dt * (pc4.x - pleft);
+                    if (FULL || c0 + 1 < w) v4.y = v4.y - dt * (pc4.y - pc4.x);
+                    if (FULL || c0 + 2 < w) v4.z = v4.z - dt * (pc4.z - pc4.y);
+                    if (FULL || c0 + 3 < w) v4.w = v4.w - dt * (pc4.w - pc4.z);
+                    zsts4(sv + i * FZ_PV + c0, v4);
+                }
+                pabove = pc4;
+            }
+        }
+        __syncthreads();
+
+        // ---- a10/a11 advection (cyclic mapping): u by (u, v); v by (u', v); density by (u', v'), decay  :166-171
+        {
+            float R[FZ_R][4];
+            float X = 0.f;
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = r0 + r, j = lane + 32 * k;
+                    R[r][k] = (FULL || (i <= h && j < w)) ? zadvect_cell<FZ_PU>(su, h + 1, w, su, sv, h, w, i, j, dt) : 0.f;
+                }
+            if (xu) X = zadvect_cell<FZ_PU>(su, h + 1, w, su, sv, h, w, 128, xe, dt);
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = r0 + r, j = lane + 32 * k;
+                    if (FULL || (i <= h && j < w)) su[i * FZ_PU + j] = R[r][k];
+                }
+            if (xu) su[128 * FZ_PU + xe] = X;
+            __syncthreads();
+
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = r0 + r, j = lane + 32 * k;
+                    R[r][k] = (FULL || (i < h && j <= w)) ? zadvect_cell<FZ_PV>(sv, h, w + 1, su, sv, h, w, i, j, dt) : 0.f;
+                }
+            if (xv) X = zadvect_cell<FZ_PV>(sv, h, w + 1, su, sv, h, w, xe, 128, dt);
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = r0 + r, j = lane + 32 * k;
+                    if (FULL || (i < h && j <= w)) sv[i * FZ_PV + j] = R[r][k];
+                }
+            if (xv) sv[xe * FZ_PV + 128] = X;
+            __syncthreads();
+
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = r0 + r, j = lane + 32 * k;
+                    R[r][k] = (FULL || (i < h && j < w)) ? zadvect_cell<FZ_PD>(sd, h, w, su, sv, h, w, i, j, dt) * a.decay : 0.f;
+                }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = r0 + r, j = lane + 32 * k;
+                    if (FULL || (i < h && j < w)) sd[i * FZ_PD + j] = R[r][k];
+                }
+            __syncthreads();
+        }
+
+        // ---- a11 returned copy of this step + buoyancy of the next
+        float* frame = a.frames ? a.frames + b * a.frame_batch_stride + (size_t)t * a.frame_step_stride : nullptr;
+        frame_and_buoyancy(frame, t + 1 < a.nsteps);
+        __syncthreads();
+    }
+
+    // ---- write back: pressure from registers, u, v, density from shared memory ------------------------------
+#pragma unroll
+    for (int r = 0; r < FZ_R; ++r) {
+        const int i = r0 + r;
+        if (i < h && colin) *reinterpret_cast<float4*>(gP + (size_t)i * pc + c0) = P[r];
+    }
+    {
+        const int gu4 = pu >> 2, gv4 = pv >> 2, gc4 = pc >> 2;
+        for (int k = tid; k < (h + 1) * gu4; k += FZ_THREADS) {
+            const int i = k / gu4, g = k - i * gu4;
+            *reinterpret_cast<float4*>(gU + (size_t)i * pu + 4 * g) = zlds4(su + i * FZ_PU + 4 * g);
+        }
+        for (int k = tid; k < h * gv4; k += FZ_THREADS) {
+            const int i = k / gv4, g = k - i * gv4;
+            *reinterpret_cast<float4*>(gV + (size_t)i * pv + 4 * g) = zlds4(sv + i * FZ_PV + 4 * g);
+        }
+        for (int k = tid; k < h * gc4; k += FZ_THREADS) {
+            const int i = k / gc4, g = k - i * gc4;
+            *reinterpret_cast<float4*>(gD + (size_t)i * pc + 4 * g) = zlds4(sd + i * FZ_PD + 4 * g);
+        }
+    }
+}
+
+bool fused_supported(const smk_grid_t* g)
+{
+    return g->h >= 2 && g->w >= 2 && g->h <= 128 && g->w <= 128 && g->pitch_u <= FZ_PU && g->pitch_v <= FZ_PV && g->pitch_c <= FZ_PD &&
+           (g->gh == 0 || (g->gh == g->h && g->row0 == 0));
+}
+
+int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float* p, int nsteps, float* frames,
+                       int64_t frame_step_stride, int64_t frame_batch_stride, const float* fmul,
+                       float dt, float c_uv, float c_d, float decay, int K, cudaStream_t s)
+{
+    if (!fused_supported(g)) return fail(SMK_EUNSUPPORTED, "k_step_fused: needs a non-slab grid of at most 128 x 128 cells, got %d x %d", g->h, g->w);
+    if (nsteps <= 0) return SMK_OK;
+    const bool full = g->h == 128 && g->w == 128 && g->pitch_u == 128 && g->pitch_v == 132 && g->pitch_c == 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_step_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM);
+        if (e != cudaSuccess) return fail((int)e, "k_step_fused: cannot opt in to %zu B of shared memory: %s", FZ_SMEM, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    FusedArgs a;
+    a.U = u; a.V = v; a.D = d; a.P = p; a.frames = frames; a.fmul = fmul;
+    a.h = g->h; a.w = g->w; a.pu = g->pitch_u; a.pv = g->pitch_v; a.pc = g->pitch_c;
+    a.su_ = g->stride_u; a.sv_ = g->stride_v; a.sc_ = g->stride_c;
+    a.frame_step_stride = frame_step_stride; a.frame_batch_stride = frame_batch_stride;
+    a.dt = dt; a.c_uv = c_uv; a.c_d = c_d; a.decay = decay; a.K = K; a.nsteps = nsteps;
+    ProfScope prof_(SMK_PH_STEP_FUSED, s);
+    if (full) k_step_fused<true><<<g->batch, FZ_THREADS, FZ_SMEM, s>>>(a);
+    else      k_step_fused<false><<<g->batch, FZ_THREADS, FZ_SMEM, s>>>(a);
+    return check_launch("k_step_fused");
+}
+
+}  // namespace smk

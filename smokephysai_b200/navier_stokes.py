@@ -6,7 +6,9 @@ methods (setup_grid, add_smoke_source, diffusion_step, advection_step, interpola
 bilinear_interpolate, pressure_projection, step) as the reference class, so callers written against
 `src.physics.navier_stokes` run unchanged.  Keyword-only extensions (reference defaults):
 `jacobi_iters=20` (the literal at navier_stokes.py:139), `batch=1` (independent simulations; fields gain
-a leading dimension when batch > 1), `sweeps_per_launch=0` (temporal-blocking depth, 0 = library default).
+a leading dimension when batch > 1), `sweeps_per_launch=0` (temporal-blocking depth, 0 = library default),
+`step_kernel="auto"` ("fused": whole simulation on one SM, all steps of a call in one launch, grids up to
+128 x 128; "phases": one kernel per phase; "auto": fused when the grid qualifies -- bit-identical results).
 
 There is no CPU compute path.  `device='cpu'` (benchmark.py:260 passes it) only means "hand results back
 as CPU tensors": the step always runs on the current CUDA device.
@@ -91,7 +93,7 @@ class NavierStokesSimulator(nn.Module):
     """Simplified Navier-Stokes smoke solver (reference: navier_stokes.py:6)."""
 
     def __init__(self, grid_size=(128, 128), dt=0.01, viscosity=0.001, device="cuda", *,
-                 jacobi_iters=20, batch=1, sweeps_per_launch=0, _slab=None):
+                 jacobi_iters=20, batch=1, sweeps_per_launch=0, step_kernel="auto", _slab=None):
         super().__init__()
         self.grid_size = grid_size
         self.dt = dt
@@ -101,6 +103,9 @@ class NavierStokesSimulator(nn.Module):
         self.jacobi_iters = int(jacobi_iters)
         self.batch = int(batch)
         self.sweeps_per_launch = int(sweeps_per_launch)
+        if step_kernel not in _lib.STEP_KERNELS:
+            raise ValueError("step_kernel must be one of %s, got %r" % (sorted(_lib.STEP_KERNELS), step_kernel))
+        self.step_kernel = step_kernel
         self._cuda, self._out_device = resolve_devices(device)
         self._lib = _lib.load()
         row0, gh = _slab if _slab is not None else (0, 0)   # (global row of local row 0, global rows): slab.py
@@ -171,7 +176,15 @@ class NavierStokesSimulator(nn.Module):
     def _params(self):
         dt, nu = float(self.dt), float(self.viscosity)
         # c = float32(dt*viscosity): the Python-double product of navier_stokes.py:72; density uses viscosity*0.1 (:160)
-        return Params(dt, dt * nu, dt * (nu * 0.1), 0.995, int(self.jacobi_iters), int(self.sweeps_per_launch))
+        return Params(dt, dt * nu, dt * (nu * 0.1), 0.995, int(self.jacobi_iters), int(self.sweeps_per_launch),
+                      _lib.STEP_KERNELS[self.step_kernel])
+
+    def step_is_fused(self):
+        """True when step() / run_steps() take the single-launch on-chip path for this grid."""
+        flag = C.c_int32(0)
+        prm = self._params()
+        _lib.call("smk_step_is_fused", C.byref(self._grid), C.byref(prm), C.byref(flag))
+        return bool(flag.value)
 
     def _to_out(self, t):
         return t if self._out_device.type == "cuda" else t.to(self._out_device)
@@ -349,6 +362,17 @@ class NavierStokesSimulator(nn.Module):
                   fr.data_ptr() if fr is not None else None, L.h * L.pitch_c, nsteps * L.h * L.pitch_c,
                   fmul.data_ptr() if fmul is not None else None, self._stream())
         return self._finish_frames(fr) if fr is not None else None
+
+    def run_steps_time_major(self, nsteps, out, fmul=None):
+        """nsteps consecutive steps whose frames go to `out`, a contiguous fp32 [nsteps, batch, h, pitch_c] device
+        buffer owned by the caller (time-major: the frames of one step are one contiguous block)."""
+        L = self._layout
+        if (tuple(out.shape) != (nsteps, L.batch, L.h, L.pitch_c) or not out.is_contiguous()
+                or out.dtype != torch.float32 or out.device != self._cuda):
+            raise ValueError("out must be a contiguous fp32 [%d, %d, %d, %d] tensor on %s" % (nsteps, L.batch, L.h, L.pitch_c, self._cuda))
+        prm = self._params()
+        _lib.call("smk_run_steps", C.byref(self._grid), C.byref(self._state), C.byref(prm), int(nsteps), out.data_ptr(),
+                  L.batch * L.h * L.pitch_c, L.h * L.pitch_c, fmul.data_ptr() if fmul is not None else None, self._stream())
 
     def divergence_norms(self):
         """(max|div|, ||div||_2) of the un-normalised divergence of the live (u, v), per simulation: [batch, 2] on the host."""

@@ -4,7 +4,7 @@ methods (add_incense_source, simulate_step, get_chaos_features, compute_*).
 
 simulate_step() is ONE pass of the CUDA step with the fractal multiply fused into the returned copy
 (the reference: ns.step() + ~960 eager launches of fractal recompute).
-Keyword-only extensions: jacobi_iters, batch, sweeps_per_launch (forwarded to NavierStokesSimulator), and
+Keyword-only extensions: jacobi_iters, batch, sweeps_per_launch, step_kernel (forwarded to NavierStokesSimulator), and
 generate_sequences() -- the batched back-end of data_loader.py:37-99.
 """
 import numpy as np
@@ -20,10 +20,10 @@ class SmokeSimulator(nn.Module):
     """Complete smoke physics simulation system (reference: smoke_simulator.py:8)."""
 
     def __init__(self, grid_size=(128, 128), dt=0.01, viscosity=0.001, device="cuda", *,
-                 jacobi_iters=20, batch=1, sweeps_per_launch=0):
+                 jacobi_iters=20, batch=1, sweeps_per_launch=0, step_kernel="auto"):
         super().__init__()
         self.ns_solver = NavierStokesSimulator(grid_size, dt, viscosity, device, jacobi_iters=jacobi_iters,
-                                               batch=batch, sweeps_per_launch=sweeps_per_launch)
+                                               batch=batch, sweeps_per_launch=sweeps_per_launch, step_kernel=step_kernel)
         self.fractal_gen = FractalGenerator(device)
         self.device = device
         self.history = []          # smoke_simulator.py:23
@@ -45,7 +45,7 @@ class SmokeSimulator(nn.Module):
         return density
 
     # -------------------------------------------------------------- batched generation (data_loader.py:37-99)
-    def generate_sequences(self, emitters, sequence_length=20, add_fractal=True, to_host=False):
+    def generate_sequences(self, emitters, sequence_length=20, add_fractal=True, to_host=False, steps_per_copy=None):
         """Reset, splat one emitter list per simulation, run sequence_length steps.
 
         emitters[b] = [((x, y), intensity), ...] for simulation b (len == batch).  Returns frames
@@ -53,10 +53,12 @@ class SmokeSimulator(nn.Module):
         sample['sequence'] (data_loader.py:66-68, :91).  History/chaos features are not touched.
 
         to_host=True hands the frames back in pinned host memory (the dataset is pickled from the host,
-        data_loader.py:33-34): the frames of step t are copied device->host on a second stream while step
-        t+1 computes, from a time-major [sequence_length, batch, h, w] device buffer so every copy is one
-        contiguous block.  The returned tensor is the [batch, sequence_length, h, w] view of the pinned
-        time-major buffer, which this simulator owns and reuses on the next call."""
+        data_loader.py:33-34): the frames of a chunk of steps are copied device->host on a second stream
+        while the next chunk computes, from a time-major [sequence_length, batch, h, w] device buffer so every
+        copy is one contiguous block.  steps_per_copy is the chunk length (default: 1 for the phase-per-kernel
+        step, 2 when the fused kernel keeps the state on chip across the steps of a launch).  The returned
+        tensor is the [batch, sequence_length, h, w] view of the pinned time-major buffer, which this
+        simulator owns and reuses on the next call."""
         ns = self.ns_solver
         L = ns._layout
         B, T = ns.batch, int(sequence_length)
@@ -76,13 +78,15 @@ class SmokeSimulator(nn.Module):
         dev, host, cs = self._gen_dev, self._gen_host, self._gen_copy_stream
         main = torch.cuda.current_stream(ns._cuda)
         cs.wait_stream(main)                      # the previous call's consumer is done with the buffers
-        for t in range(T):
-            ns.step_into(dev[t], fmul=fmul)
+        n = int(steps_per_copy) if steps_per_copy else (2 if ns.step_is_fused() else 1)
+        for t in range(0, T, n):
+            m = min(n, T - t)
+            ns.run_steps_time_major(m, dev[t:t + m], fmul=fmul)
             ev = torch.cuda.Event()
             ev.record(main)
             cs.wait_event(ev)
             with torch.cuda.stream(cs):
-                host[t].copy_(dev[t], non_blocking=True)
+                host[t:t + m].copy_(dev[t:t + m], non_blocking=True)
         cs.synchronize()
         return host.permute(1, 0, 2, 3)[..., :L.w]
 

@@ -1,0 +1,153 @@
+"""GPU parity of the fused whole-step kernel (csrc/fused.cu: the simulation on one SM, n steps per launch)
+against the CPU oracle and against the phase-per-kernel path, through the same class surface / C ABI.
+
+Tolerance: none -- every field must be numerically equal (fp32, no FMA, same association).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import assert_same, emitters_for_sequence
+
+pytestmark = pytest.mark.gpu
+
+from smokephysai_b200 import NavierStokesSimulator, SmokeSimulator, _lib  # noqa: E402
+
+FIELDS = ("u", "v", "p", "density")
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def make(h, w, dt=0.01, nu=0.001, K=20, **kw):
+    return NavierStokesSimulator((h, w), dt, nu, "cuda", jacobi_iters=K, **kw)
+
+
+def random_state(h, w, seed, vel=300.0):
+    rng = np.random.default_rng(seed)
+    return {
+        "u": ((rng.random((h + 1, w)) - 0.5) * vel).astype(np.float32),
+        "v": ((rng.random((h, w + 1)) - 0.5) * vel).astype(np.float32),
+        "p": rng.standard_normal((h, w)).astype(np.float32),
+        "density": rng.random((h, w)).astype(np.float32),
+    }
+
+
+def test_dispatch_rules():
+    assert make(128, 128).step_is_fused()
+    assert make(2, 2).step_is_fused()
+    assert make(96, 40, batch=3).step_is_fused()
+    assert not make(128, 128, step_kernel="phases").step_is_fused()
+    assert not make(129, 128).step_is_fused()
+    assert not make(128, 132).step_is_fused()
+    assert not make(1, 64).step_is_fused()
+    with pytest.raises(_lib.SmokeLibraryError, match="128 x 128"):
+        make(256, 256, step_kernel="fused").step()
+    with pytest.raises(ValueError):
+        make(64, 64, step_kernel="tensor-cores")
+
+
+@pytest.mark.parametrize("h,w,K", [
+    (128, 128, 20), (128, 128, 0), (128, 128, 1), (128, 128, 7), (2, 2, 5), (3, 3, 4), (5, 128, 9), (128, 5, 9), (127, 127, 12),
+    (128, 96, 10), (96, 128, 10), (128, 127, 6), (127, 128, 6), (64, 64, 20), (33, 100, 11), (100, 33, 11), (8, 8, 3), (9, 4, 3),
+])
+def test_fused_step_vs_oracle_and_phases(h, w, K):
+    """Random fields with back-traces of several cells (|dt*vel| up to 3) so gathers cross warps and hit the clamps."""
+    st = random_state(h, w, h * 1000 + w)
+    ref = oracle.OracleSolver((h, w), 0.02, 0.01, K)
+    fz = make(h, w, 0.02, 0.01, K, step_kernel="fused")
+    ph = make(h, w, 0.02, 0.01, K, step_kernel="phases")
+    assert fz.step_is_fused() and not ph.step_is_fused()
+    for k in FIELDS:
+        setattr(ref, k, st[k].copy())
+        setattr(fz, k, T(st[k]))
+        setattr(ph, k, T(st[k]))
+    for t in range(3):
+        fr_ref = ref.step()
+        fr_fz = fz.step()
+        fr_ph = ph.step()
+        for k in FIELDS:
+            assert_same(N(getattr(fz, k)), getattr(ref, k), "%dx%d K=%d step %d fused vs oracle %s" % (h, w, K, t, k))
+            assert_same(N(getattr(fz, k)), N(getattr(ph, k)), "%dx%d K=%d step %d fused vs phases %s" % (h, w, K, t, k))
+        assert_same(N(fr_fz), fr_ref, "returned frame vs oracle")
+        assert_same(N(fr_fz), N(fr_ph), "returned frame vs phases")
+
+
+@pytest.mark.parametrize("h,w", [(128, 128), (60, 128), (128, 52)])
+def test_fused_multi_step_launch_equals_single_steps(h, w):
+    """run_steps(n) is ONE launch that keeps the state on chip; it must equal n single-step launches, the phase
+    path and the oracle -- frames, final fields and the padding columns of the arena."""
+    B, n, K = 3, 7, 15
+    sims = {k: make(h, w, 0.02, 0.005, K, batch=B, step_kernel=k) for k in ("fused", "phases")}
+    one = make(h, w, 0.02, 0.005, K, batch=B, step_kernel="fused")
+    states = [random_state(h, w, 77 + b, vel=120.0) for b in range(B)]
+    for s in list(sims.values()) + [one]:
+        for k in FIELDS:
+            setattr(s, k, T(np.stack([st[k] for st in states])))
+    fmul = torch.rand(h, sims["fused"]._layout.pitch_c, device="cuda") * 0.05
+    n0 = _lib.launch_count()
+    fr_fz = sims["fused"].run_steps(n, fmul=fmul)
+    assert _lib.launch_count() - n0 == 1
+    fr_ph = sims["phases"].run_steps(n, fmul=fmul)
+    fr_one = torch.stack([one.step(fmul=fmul) for _ in range(n)], dim=1)
+    assert_same(N(fr_fz), N(fr_ph), "frames fused vs phases")
+    assert_same(N(fr_fz), N(fr_one), "frames one launch vs n launches")
+    for k in FIELDS:
+        assert_same(N(getattr(sims["fused"], k)), N(getattr(sims["phases"], k)), k + " fused vs phases")
+        assert_same(N(getattr(sims["fused"], k)), N(getattr(one, k)), k + " one launch vs n launches")
+    # the oracle on simulation 1 (no fractal multiplier on its frames: compare fields only)
+    ref = oracle.OracleSolver((h, w), 0.02, 0.005, K)
+    for k in FIELDS:
+        setattr(ref, k, states[1][k].copy())
+    for _ in range(n):
+        ref.step()
+    for k in FIELDS:
+        assert_same(N(getattr(sims["fused"], k))[1], getattr(ref, k), k + " vs oracle")
+    # padding columns of the live arena fields stay zero (the float4 kernels rely on it)
+    fz = sims["fused"]
+    L = fz._layout
+    for name in ("u", "v", "d", "p"):
+        cur = getattr(fz._state, "cur_" + name)
+        rows, cols, pitch = L.shape_of("%s%d" % (name, cur))
+        off = L.offset["%s%d" % (name, cur)]
+        full = fz._arena[off: off + L.batch * rows * pitch].view(L.batch, rows, pitch)
+        assert not full[:, :, cols:].any(), "padding of %s" % name
+
+
+def test_fused_time_major_frames_and_generate_sequences():
+    B, L = 6, 9
+    ems = [[((x, y), i) for x, y, _, i in emitters_for_sequence(s)] for s in range(B)]
+    fz = SmokeSimulator((128, 128), device="cuda", batch=B, jacobi_iters=40, step_kernel="fused")
+    ph = SmokeSimulator((128, 128), device="cuda", batch=B, jacobi_iters=40, step_kernel="phases")
+    a = N(fz.generate_sequences(ems, L))
+    b = N(ph.generate_sequences(ems, L))
+    assert_same(a, b, "generate_sequences fused vs phases")
+    for spc in (None, 1, 4, 9, 20):
+        h_ = fz.generate_sequences(ems, L, to_host=True, steps_per_copy=spc)
+        assert h_.is_pinned() and tuple(h_.shape) == (B, L, 128, 128)
+        assert_same(h_.numpy(), a, "to_host, steps_per_copy=%r" % spc)
+
+
+def test_fused_c2_full_size_vs_oracle():
+    """BASELINE config 2 at full size: 256 x 128^2, K=40, 20 steps in ONE launch; six sequences against the oracle."""
+    B, K, steps = 256, 40, 20
+    ns = make(128, 128, K=K, batch=B, step_kernel="fused")
+    ns.add_sources([emitters_for_sequence(s) for s in range(B)])
+    d0 = N(ns.density).copy()
+    frames = ns.run_steps(steps)
+    u, v, p, d = (N(getattr(ns, k)) for k in FIELDS)
+    sel = [0, 1, 147, 148, 200, 255]
+    ou = np.zeros((len(sel), 129, 128), np.float32); ov = np.zeros((len(sel), 128, 129), np.float32)
+    op = np.zeros((len(sel), 128, 128), np.float32); od = d0[sel].copy()
+    ofr = oracle.run_batch(ou, ov, op, od, 0.01, 0.001, K, steps, nthreads=4)
+    for n_, s in enumerate(sel):
+        assert_same(u[s], ou[n_], "u seq %d" % s); assert_same(v[s], ov[n_], "v seq %d" % s)
+        assert_same(p[s], op[n_], "p seq %d" % s); assert_same(d[s], od[n_], "d seq %d" % s)
+        assert_same(N(frames[s]), ofr[n_], "frames seq %d" % s)
+    assert not d[:, -1, :].any() and not d[:, :, -1].any()
