@@ -26,7 +26,16 @@ namespace smk {
 constexpr int FZ_R = 8, FZ_NW = 16, FZ_THREADS = FZ_NW * 32;
 constexpr int FZ_PU = 128, FZ_PV = 132, FZ_PD = 128;                 // shared-memory row pitches
 constexpr int FZ_SU = 129 * FZ_PU, FZ_SV = 128 * FZ_PV, FZ_SD = 128 * FZ_PD;     // floats
+constexpr int FZ_PMASK = 6;       // row pairs 1 and 2 of a sweep use f32x2 arithmetic, 0 and 3 scalar (fastest mix measured)
 constexpr size_t FZ_SMEM = (size_t)(FZ_SU + FZ_SV + FZ_SD) * 4 + sizeof(float4) * 2 * 2 * FZ_NW * 32;
+
+// Phase timing for tools/micro/fused_probe.cu only (never defined in the library build): thread 0 of CTA 0
+// accumulates clock64() deltas per phase into FusedArgs::ticks.
+#ifdef SMK_FUSED_TIMING
+#define FZ_TICK(k) do { if (tid == 0 && blockIdx.x == 0) { const long long t1_ = clock64(); a.ticks[k] += t1_ - tick0_; tick0_ = t1_; } } while (0)
+#else
+#define FZ_TICK(k) do { } while (0)
+#endif
 
 struct FusedArgs {
     float* U; float* V; float* D; float* P;              // live state, updated in place
@@ -35,6 +44,9 @@ struct FusedArgs {
     long long su_, sv_, sc_, frame_step_stride, frame_batch_stride;
     float dt, c_uv, c_d, decay;
     int K, nsteps;
+#ifdef SMK_FUSED_TIMING
+    long long* ticks;
+#endif
 };
 
 __device__ __forceinline__ float4 zlds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -131,6 +143,9 @@ k_step_fused(const FusedArgs a)
     const bool xu = (h == 128) && lane < 8 && xe < w;
     const bool xv = (w == 128) && lane < 8 && xe < h;
     const float dt = a.dt;
+#ifdef SMK_FUSED_TIMING
+    long long tick0_ = clock64();
+#endif
 
     // ---- load the state: u, v, density to shared memory, pressure to registers ---------------------------
     if (!FULL) {
@@ -152,18 +167,22 @@ k_step_fused(const FusedArgs a)
             zsts4(sd + i * FZ_PD + 4 * g, *reinterpret_cast<const float4*>(gD + (size_t)i * pc + 4 * g));
         }
     }
-    float4 P[FZ_R];
+    // pressure: the packed register strip of jacobi_core.cuh (a float2 pairs row r with row r + 4)
+    PackedStrip P;
     const bool colin = c0 < pc;
+    unsigned ringmask = 0;              // rows of the strip on the Dirichlet ring or outside the grid
 #pragma unroll
     for (int r = 0; r < FZ_R; ++r) {
         const int i = r0 + r;
-        P[r] = (colin && i < h) ? *reinterpret_cast<const float4*>(gP + (size_t)i * pc + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        packed_set_row(P, r, (colin && i < h) ? *reinterpret_cast<const float4*>(gP + (size_t)i * pc + c0) : make_float4(0.f, 0.f, 0.f, 0.f));
+        if (i < 1 || i > h - 2) ringmask |= 1u << r;
     }
-    const float cm0 = (c0 + 0 >= 1 && c0 + 0 <= w - 2) ? 0.25f : 0.f;
-    const float cm1 = (c0 + 1 >= 1 && c0 + 1 <= w - 2) ? 0.25f : 0.f;
-    const float cm2 = (c0 + 2 >= 1 && c0 + 2 <= w - 2) ? 0.25f : 0.f;
-    const float cm3 = (c0 + 3 >= 1 && c0 + 3 <= w - 2) ? 0.25f : 0.f;
-    const bool fast = (r0 >= 1) && (r0 + FZ_R - 1 <= h - 2);
+    float2 M[4];                        // 0.25 inside, 0 on the ring columns / outside
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float m = (c0 + c >= 1 && c0 + c <= w - 2) ? 0.25f : 0.f;
+        M[c] = make_float2(m, m);
+    }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
@@ -197,6 +216,7 @@ k_step_fused(const FusedArgs a)
 
     if (a.nsteps > 0) frame_and_buoyancy(nullptr, true);
     __syncthreads();
+    FZ_TICK(0);
 
     for (int t = 0; t < a.nsteps; ++t) {
         // ---- a4 diffusion of u (rows 0..h), v (cols 0..w), density                    navier_stokes.py:158-160
@@ -255,8 +275,9 @@ k_step_fused(const FusedArgs a)
             __syncthreads();
         }
 
+        FZ_TICK(1);
         // ---- a5 divergence into registers: (((u[i+1][j] - u[i][j]) + v[i][j+1]) - v[i][j]) / dt           :136
-        float4 Dv[FZ_R];
+        PackedStrip ND;                 // minus the divergence (x - div == x + (-div))
         {
             float4 ua = zlds4(su + r0 * FZ_PU + c0);
 #pragma unroll
@@ -277,26 +298,44 @@ k_step_fused(const FusedArgs a)
                     if (c0 + 2 >= w) o.z = 0.f;
                     if (c0 + 3 >= w) o.w = 0.f;
                 }
-                Dv[r] = o;
+                packed_set_row(ND, r, make_float4(-o.x, -o.y, -o.z, -o.w));
                 ua = ub;
             }
         }
 
-        // ---- a6 K Jacobi sweeps on the register tile (see jacobi.cu)                                  :139-145
-        halo[0][0][warp][lane] = P[0];
-        halo[0][1][warp][lane] = P[FZ_R - 1];
+        FZ_TICK(2);
+        // ---- a6 K Jacobi sweeps on the register tile (see jacobi.cu / jacobi_core.cuh)                :139-145
+        // two sweeps per trip, ping-pong between the register sets P and Q; sweep s reads halo[s & 1]
+        halo[0][0][warp][lane] = packed_row(P, 0);
+        halo[0][1][warp][lane] = packed_row(P, 7);
         __syncthreads();
-        for (int s = 0; s < a.K; ++s) {
-            const int buf = s & 1;
-            const float4 up = warp > 0 ? halo[buf][1][warp - 1][lane] : zero4;
-            const float4 dn = warp < FZ_NW - 1 ? halo[buf][0][warp + 1][lane] : zero4;
-            float4* pf = &halo[buf ^ 1][0][warp][lane];
-            float4* pl = &halo[buf ^ 1][1][warp][lane];
-            if (fast) sweep_rows<FZ_R, true>(P, Dv, up, dn, cm0, cm1, cm2, cm3, r0, h, pf, pl);
-            else      sweep_rows<FZ_R, false>(P, Dv, up, dn, cm0, cm1, cm2, cm3, r0, h, pf, pl);
-            __syncthreads();
+        {
+            PackedStrip Q;
+            int s = 0;
+            for (; s + 1 < a.K; s += 2) {
+                {
+                    const float4 up = warp > 0 ? halo[0][1][warp - 1][lane] : zero4;
+                    const float4 dn = warp < FZ_NW - 1 ? halo[0][0][warp + 1][lane] : zero4;
+                    sweep_packed<FZ_PMASK>(P, Q, ND, up, dn, M, ringmask, &halo[1][0][warp][lane], &halo[1][1][warp][lane]);
+                    __syncthreads();
+                }
+                {
+                    const float4 up = warp > 0 ? halo[1][1][warp - 1][lane] : zero4;
+                    const float4 dn = warp < FZ_NW - 1 ? halo[1][0][warp + 1][lane] : zero4;
+                    sweep_packed<FZ_PMASK>(Q, P, ND, up, dn, M, ringmask, &halo[0][0][warp][lane], &halo[0][1][warp][lane]);
+                    __syncthreads();
+                }
+            }
+            if (s < a.K) {                  // odd K: one more sweep, the result moves back into P
+                const float4 up = warp > 0 ? halo[0][1][warp - 1][lane] : zero4;
+                const float4 dn = warp < FZ_NW - 1 ? halo[0][0][warp + 1][lane] : zero4;
+                sweep_packed<FZ_PMASK>(P, Q, ND, up, dn, M, ringmask, &halo[1][0][warp][lane], &halo[1][1][warp][lane]);
+                P = Q;
+                __syncthreads();
+            }
         }
 
+        FZ_TICK(3);
         // ---- a7 gradient subtract, in place on the thread's strip                                     :148-149
         {
             // halo[K & 1][1][warp - 1] holds the final last row of the warp above: the "row above" of row r0
@@ -304,7 +343,7 @@ k_step_fused(const FusedArgs a)
 #pragma unroll
             for (int r = 0; r < FZ_R; ++r) {
                 const int i = r0 + r;
-                const float4 pc4 = P[r];
+                const float4 pc4 = packed_row(P, r);
                 const float pleft = __shfl_up_sync(0xffffffffu, pc4.w, 1);
                 if (FULL || (i < h && colin)) {
                     float4 u4 = zlds4(su + i * FZ_PU + c0);
@@ -327,6 +366,7 @@ k_step_fused(const FusedArgs a)
         }
         __syncthreads();
 
+        FZ_TICK(4);
         // ---- a10/a11 advection (cyclic mapping): u by (u, v); v by (u', v); density by (u', v'), decay  :166-171
         {
             float R[FZ_R][4];
@@ -387,17 +427,19 @@ k_step_fused(const FusedArgs a)
             __syncthreads();
         }
 
+        FZ_TICK(5);
         // ---- a11 returned copy of this step + buoyancy of the next
         float* frame = a.frames ? a.frames + b * a.frame_batch_stride + (size_t)t * a.frame_step_stride : nullptr;
         frame_and_buoyancy(frame, t + 1 < a.nsteps);
         __syncthreads();
+        FZ_TICK(6);
     }
 
     // ---- write back: pressure from registers, u, v, density from shared memory ------------------------------
 #pragma unroll
     for (int r = 0; r < FZ_R; ++r) {
         const int i = r0 + r;
-        if (i < h && colin) *reinterpret_cast<float4*>(gP + (size_t)i * pc + c0) = P[r];
+        if (i < h && colin) *reinterpret_cast<float4*>(gP + (size_t)i * pc + c0) = packed_row(P, r);
     }
     {
         const int gu4 = pu >> 2, gv4 = pv >> 2, gc4 = pc >> 2;
@@ -414,6 +456,7 @@ k_step_fused(const FusedArgs a)
             *reinterpret_cast<float4*>(gD + (size_t)i * pc + 4 * g) = zlds4(sd + i * FZ_PD + 4 * g);
         }
     }
+    FZ_TICK(7);
 }
 
 bool fused_supported(const smk_grid_t* g)

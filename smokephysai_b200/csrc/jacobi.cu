@@ -87,64 +87,15 @@ k_jacobi(const float* __restrict__ pin, float* __restrict__ pout, const float* _
     }
 }
 
-// Packed variant (sm_100 add.f32x2 / mul.f32x2 through __fadd2_rn / __fmul2_rn: two IEEE-rounded fp32 results
-// per instruction, so half the issue slots for the same arithmetic).  A float2 pairs row rr of the warp's strip
-// with row rr + R/2, which keeps every stencil neighbour of a pair aligned in another pair (up of (rr, rr+R/2) is
-// (rr-1, rr-1+R/2)); only the seam between the two half strips needs a repack per sweep.  x - d is x + (-d), so
-// the divergence is held negated.  The Dirichlet ring / out-of-domain rows are zeroed after the sweep (ringmask).
-template <int R>
-struct PackedStrip {
-    float2 Q[R / 2][4];      // pressure: Q[rr][c] = (p[rr][c], p[rr + R/2][c])
-    float2 ND[R / 2][4];     // minus divergence, same pairing
-};
-
-template <int R>
-__device__ __forceinline__ void sweep_rows_packed(PackedStrip<R>& S, const float4 uph, const float4 dnh,
-                                                  const float2 (&M)[4], const unsigned ringmask)
-{
-    constexpr int H = R / 2;
-    // seam pairs: up of row 0 / row H, down of row H-1 / row R-1
-    float2 up[4] = {make_float2(uph.x, S.Q[H - 1][0].x), make_float2(uph.y, S.Q[H - 1][1].x),
-                    make_float2(uph.z, S.Q[H - 1][2].x), make_float2(uph.w, S.Q[H - 1][3].x)};
-    const float2 dnl[4] = {make_float2(S.Q[0][0].y, dnh.x), make_float2(S.Q[0][1].y, dnh.y),
-                           make_float2(S.Q[0][2].y, dnh.z), make_float2(S.Q[0][3].y, dnh.w)};
-#pragma unroll
-    for (int rr = 0; rr < H; ++rr) {
-        float2 cur[4] = {S.Q[rr][0], S.Q[rr][1], S.Q[rr][2], S.Q[rr][3]};
-        float2 left, right;
-        left.x = __shfl_up_sync(0xffffffffu, cur[3].x, 1);
-        left.y = __shfl_up_sync(0xffffffffu, cur[3].y, 1);
-        right.x = __shfl_down_sync(0xffffffffu, cur[0].x, 1);
-        right.y = __shfl_down_sync(0xffffffffu, cur[0].y, 1);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float2 dn = (rr < H - 1) ? S.Q[rr + 1][c] : dnl[c];
-            const float2 l = (c == 0) ? left : cur[c - 1];
-            const float2 r = (c == 3) ? right : cur[c + 1];
-            float2 t = __fadd2_rn(up[c], dn);
-            t = __fadd2_rn(t, l);
-            t = __fadd2_rn(t, r);
-            t = __fadd2_rn(t, S.ND[rr][c]);
-            S.Q[rr][c] = __fmul2_rn(M[c], t);
-            up[c] = cur[c];
-        }
-    }
-    if (ringmask) {
-#pragma unroll
-        for (int rr = 0; rr < H; ++rr) {
-            if (ringmask & (1u << rr)) { S.Q[rr][0].x = 0.f; S.Q[rr][1].x = 0.f; S.Q[rr][2].x = 0.f; S.Q[rr][3].x = 0.f; }
-            if (ringmask & (1u << (rr + H))) { S.Q[rr][0].y = 0.f; S.Q[rr][1].y = 0.f; S.Q[rr][2].y = 0.f; S.Q[rr][3].y = 0.f; }
-        }
-    }
-}
-
-template <int R, int NW>
+// Packed variant (see jacobi_core.cuh): add.f32x2 / mul.f32x2 halve the FP32 issue slots of a sweep.  The strip is
+// always 8 rows per thread (R == 8); sweeps ping-pong between two register sets, two sweeps per loop trip.
+template <int R, int NW, int PMASK>
 __global__ void __launch_bounds__(NW * 32, (NW * 32 <= 256) ? 2 : 1)
 k_jacobi_packed(const float* __restrict__ pin, float* __restrict__ pout, const float* __restrict__ div,
                 const int h, const int w, const int pitch, const long long bstride,
                 const int T, const int HX, const int ox, const int oy)
 {
-    constexpr int H = R / 2;
+    static_assert(R == 8, "the packed strip pairs row r with row r + 4");
     __shared__ float4 halo[2][2][NW][32];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -154,7 +105,7 @@ k_jacobi_packed(const float* __restrict__ pin, float* __restrict__ pout, const f
     const size_t boff = (size_t)blockIdx.z * (size_t)bstride;
     pin += boff; pout += boff; div += boff;
 
-    PackedStrip<R> S;
+    PackedStrip A, B, ND;
     const bool colin = gj < pitch;
     unsigned ringmask = 0;
 #pragma unroll
@@ -166,14 +117,8 @@ k_jacobi_packed(const float* __restrict__ pin, float* __restrict__ pout, const f
             d4 = __ldg(reinterpret_cast<const float4*>(div + (size_t)gi * pitch + gj));
         }
         if (gi < 1 || gi > h - 2) ringmask |= 1u << r;
-        const int rr = r % H;
-        if (r < H) {
-            S.Q[rr][0].x = p4.x; S.Q[rr][1].x = p4.y; S.Q[rr][2].x = p4.z; S.Q[rr][3].x = p4.w;
-            S.ND[rr][0].x = -d4.x; S.ND[rr][1].x = -d4.y; S.ND[rr][2].x = -d4.z; S.ND[rr][3].x = -d4.w;
-        } else {
-            S.Q[rr][0].y = p4.x; S.Q[rr][1].y = p4.y; S.Q[rr][2].y = p4.z; S.Q[rr][3].y = p4.w;
-            S.ND[rr][0].y = -d4.x; S.ND[rr][1].y = -d4.y; S.ND[rr][2].y = -d4.z; S.ND[rr][3].y = -d4.w;
-        }
+        packed_set_row(A, r, p4);
+        packed_set_row(ND, r, make_float4(-d4.x, -d4.y, -d4.z, -d4.w));
     }
     float2 M[4];
 #pragma unroll
@@ -183,14 +128,30 @@ k_jacobi_packed(const float* __restrict__ pin, float* __restrict__ pout, const f
     }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int s = 0; s < T; ++s) {
-        const int buf = s & 1;
-        halo[buf][0][warp][lane] = make_float4(S.Q[0][0].x, S.Q[0][1].x, S.Q[0][2].x, S.Q[0][3].x);                       // row 0
-        halo[buf][1][warp][lane] = make_float4(S.Q[H - 1][0].y, S.Q[H - 1][1].y, S.Q[H - 1][2].y, S.Q[H - 1][3].y);       // row R-1
-        __syncthreads();
-        const float4 up = warp > 0 ? halo[buf][1][warp - 1][lane] : zero4;
-        const float4 dn = warp < NW - 1 ? halo[buf][0][warp + 1][lane] : zero4;
-        sweep_rows_packed<R>(S, up, dn, M, ringmask);
+    halo[0][0][warp][lane] = packed_row(A, 0);
+    halo[0][1][warp][lane] = packed_row(A, 7);
+    __syncthreads();
+    int s = 0;
+    for (; s + 1 < T; s += 2) {            // s is even here: sweep s reads halo[0], sweep s+1 reads halo[1]
+        {
+            const float4 up = warp > 0 ? halo[0][1][warp - 1][lane] : zero4;
+            const float4 dn = warp < NW - 1 ? halo[0][0][warp + 1][lane] : zero4;
+            sweep_packed<PMASK>(A, B, ND, up, dn, M, ringmask, &halo[1][0][warp][lane], &halo[1][1][warp][lane]);
+            __syncthreads();
+        }
+        {
+            const float4 up = warp > 0 ? halo[1][1][warp - 1][lane] : zero4;
+            const float4 dn = warp < NW - 1 ? halo[1][0][warp + 1][lane] : zero4;
+            const bool more = s + 2 < T;
+            sweep_packed<PMASK>(B, A, ND, up, dn, M, ringmask, more ? &halo[0][0][warp][lane] : nullptr, more ? &halo[0][1][warp][lane] : nullptr);
+            if (more) __syncthreads();
+        }
+    }
+    if (s < T) {                           // odd T: one more sweep, then move the result back into A
+        const float4 up = warp > 0 ? halo[0][1][warp - 1][lane] : zero4;
+        const float4 dn = warp < NW - 1 ? halo[0][0][warp + 1][lane] : zero4;
+        sweep_packed<PMASK>(A, B, ND, up, dn, M, ringmask, nullptr, nullptr);
+        A = B;
     }
 
     const int vx0 = x0 + (blockIdx.x > 0 ? HX : 0);
@@ -201,12 +162,8 @@ k_jacobi_packed(const float* __restrict__ pin, float* __restrict__ pout, const f
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int gi = gi0 + r;
-            const int rr = r % H;
-            if (gi >= vy0 && gi < vy1 && gi < h) {
-                const float4 o = (r < H) ? make_float4(S.Q[rr][0].x, S.Q[rr][1].x, S.Q[rr][2].x, S.Q[rr][3].x)
-                                         : make_float4(S.Q[rr][0].y, S.Q[rr][1].y, S.Q[rr][2].y, S.Q[rr][3].y);
-                *reinterpret_cast<float4*>(pout + (size_t)gi * pitch + gj) = o;
-            }
+            if (gi >= vy0 && gi < vy1 && gi < h)
+                *reinterpret_cast<float4*>(pout + (size_t)gi * pitch + gj) = packed_row(A, r);
         }
     }
 }
@@ -245,11 +202,14 @@ static int pick_T(const smk_grid_t* g, int K, int TH, int tmax, int sms)
     return bestT;
 }
 
-static bool use_packed()
+// 0: scalar in-place kernel (k_jacobi); else the ping-pong kernel (k_jacobi_packed) with this mask of row pairs
+// (bit rr) on f32x2 arithmetic.  Default 6: measured fastest on B200 (tools/micro/jacobi_probe.cu: 886 cycles per
+// sweep of a 128 x 128 tile against 928 all-scalar, 920 all-packed; the in-place k_jacobi needs ~1130).
+static int use_packed()
 {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("SMK_JACOBI_PACKED"); v = e ? atoi(e) : 0; }
-    return v != 0;
+    if (v < 0) { const char* e = getenv("SMK_JACOBI_PACKED"); v = e ? atoi(e) : 6; }
+    return v;
 }
 
 template <int R, int NW>
@@ -269,10 +229,15 @@ static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, in
         int rc;
         {
             ProfScope prof_(SMK_PH_JACOBI, s);
-            if (use_packed())
-                k_jacobi_packed<R, NW><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c, (long long)g->stride_c,
-                                                                t, HX, 128 - 2 * HX, TH - 2 * t);
-            else
+#define SMK_PACKED_CASE(M) case M: k_jacobi_packed<8, NW, M><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c, \
+                                                           (long long)g->stride_c, t, HX, 128 - 2 * HX, TH - 2 * t); break;
+            if (R == 8 && use_packed()) {
+                switch (use_packed()) {
+                    SMK_PACKED_CASE(6) SMK_PACKED_CASE(9) SMK_PACKED_CASE(2) SMK_PACKED_CASE(7) SMK_PACKED_CASE(16)
+                    default: k_jacobi_packed<8, NW, 15><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c,
+                                                           (long long)g->stride_c, t, HX, 128 - 2 * HX, TH - 2 * t);
+                }
+            } else
                 k_jacobi<R, NW><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c, (long long)g->stride_c,
                                                          t, HX, 128 - 2 * HX, TH - 2 * t);
             rc = check_launch("k_jacobi");
