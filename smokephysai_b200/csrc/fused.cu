@@ -91,6 +91,33 @@ __device__ __forceinline__ void zdiffuse_strip_full(const float* F, const float 
     }
 }
 
+// Four IEEE quotients n / d (navier_stokes.py:136 divides by dt).  nvcc's div.rn.f32 has a fast path (three FFMAs
+// around a reciprocal) and, for operands or quotients near the denormal range, a ~100-instruction subroutine; the
+// thin ring where the diffusing velocities underflow sends whole warps there every step.  Those warps take an
+// fp64 division instead: (float)((double)n / (double)d) is the correctly rounded fp32 quotient for every finite
+// n, d (53 >= 2*24 + 2 bits makes the double rounding innocuous, denormal results included: a quotient of two
+// 24-bit significands is either exactly a rounding midpoint or at least 2^-48 away from it in relative terms).
+__device__ __forceinline__ bool zdiv_odd(const float x)
+{
+    const float ax = fabsf(x);
+    return ax != 0.0f && !(ax >= 1e-30f && ax <= 1e30f);
+}
+__device__ __forceinline__ float4 zdiv4(float4 n, const float d)
+{
+#ifdef SMK_PROBE_NODIV               // tools/micro only: what the step costs without the division (wrong results)
+    n.x *= d; n.y *= d; n.z *= d; n.w *= d;
+    return n;
+#endif
+    if (__any_sync(0xffffffffu, zdiv_odd(n.x) || zdiv_odd(n.y) || zdiv_odd(n.z) || zdiv_odd(n.w))) {
+        const double dd = (double)d;
+        n.x = (float)((double)n.x / dd); n.y = (float)((double)n.y / dd);
+        n.z = (float)((double)n.z / dd); n.w = (float)((double)n.w / dd);
+    } else {
+        n.x = n.x / d; n.y = n.y / d; n.z = n.z / d; n.w = n.w / d;
+    }
+    return n;
+}
+
 // advection_step at one cell (navier_stokes.py:74-131): same restatement as k_advect (stencil.cu) with the
 // field, u and v in shared memory.  rows x cols is the advected field, h x w the cell grid.
 template <int PITCH>
@@ -115,6 +142,58 @@ __device__ __forceinline__ float zadvect_cell(const float* F, const int rows, co
     float s = (ax * ay) * q[0] + (bx * ay) * q[dx];
     s = s + (ax * by) * q[dy];
     s = s + (bx * by) * q[dy + dx];
+    return s;
+}
+
+// The same for the two cells (i, j) and (i, j + 32) of a thread's cyclic-mapped row at once, with the fp32 adds and
+// multiplies issued as f32x2 instructions (__fadd2_rn / __fmul2_rn: two IEEE-rounded results per instruction, so
+// the per-cell operation sequence and rounding are those of zadvect_cell; x - y is x + (-y)).  Clamps, floors,
+// conversions and the gathers stay scalar -- and so does every ADD THAT CONSUMES A PRODUCT: ptxas 12.9 contracts
+// mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (the scalar forms are left alone), which would
+// break the rounded-once contract.  Packed: the multiplies, and the adds whose operands are not products.  Velocity samples that the reference's interpolation zeroes are loaded as
+// 0, which makes u_i / v_i exactly 0.  `scale` (the 0.995 decay, :171) is applied when SCALE is set.
+__device__ __forceinline__ float2 zneg2(const float2 a) { return make_float2(-a.x, -a.y); }
+
+template <int PITCH, bool SCALE>
+__device__ __forceinline__ float2 zadvect_pair(const float* F, const int rows, const int cols, const float* su, const float* sv,
+                                               const int h, const int w, const int i, const int j, const float dt, const float scale)
+{
+    const int j1 = j + 32;
+    const bool cu0 = (j <= w - 2 && i <= h - 1), cu1 = (j1 <= w - 2 && i <= h - 1);
+    const bool cv0 = (i <= h - 2 && j <= w - 1), cv1 = (i <= h - 2 && j1 <= w - 1);
+    const float2 ua = make_float2(cu0 ? su[i * FZ_PU + j] : 0.f, cu1 ? su[i * FZ_PU + j1] : 0.f);
+    const float2 ub = make_float2(cu0 ? su[i * FZ_PU + j + 1] : 0.f, cu1 ? su[i * FZ_PU + j1 + 1] : 0.f);
+    const float2 va = make_float2(cv0 ? sv[i * FZ_PV + j] : 0.f, cv1 ? sv[i * FZ_PV + j1] : 0.f);
+    const float2 vb = make_float2(cv0 ? sv[(i + 1) * FZ_PV + j] : 0.f, cv1 ? sv[(i + 1) * FZ_PV + j1] : 0.f);
+    const float2 half2 = make_float2(0.5f, 0.5f), dt2 = make_float2(dt, dt), one2 = make_float2(1.0f, 1.0f);
+    const float2 hua = __fmul2_rn(half2, ua), hub = __fmul2_rn(half2, ub);
+    const float2 hva = __fmul2_rn(half2, va), hvb = __fmul2_rn(half2, vb);
+    const float2 ui = make_float2(hua.x + hub.x, hua.y + hub.y);
+    const float2 vi = make_float2(hva.x + hvb.x, hva.y + hvb.y);
+    const float xmax = (float)(cols - 1), ymax = (float)(rows - 1);
+    const float2 du = __fmul2_rn(dt2, ui), dv = __fmul2_rn(dt2, vi);
+    float2 px = make_float2((float)j - du.x, (float)j1 - du.y);
+    float2 py = make_float2((float)i - dv.x, (float)i - dv.y);
+    px.x = fminf(fmaxf(px.x, 0.0f), xmax); px.y = fminf(fmaxf(px.y, 0.0f), xmax);
+    py.x = fminf(fmaxf(py.x, 0.0f), ymax); py.y = fminf(fmaxf(py.y, 0.0f), ymax);
+    const float2 fx0 = make_float2(floorf(px.x), floorf(px.y)), fy0 = make_float2(floorf(py.x), floorf(py.y));
+    float2 fx1 = __fadd2_rn(fx0, one2), fy1 = __fadd2_rn(fy0, one2);
+    fx1.x = fminf(fx1.x, xmax); fx1.y = fminf(fx1.y, xmax);
+    fy1.x = fminf(fy1.x, ymax); fy1.y = fminf(fy1.y, ymax);
+    const float2 ax = __fadd2_rn(fx1, zneg2(px)), bx = __fadd2_rn(px, zneg2(fx0));
+    const float2 ay = __fadd2_rn(fy1, zneg2(py)), by = __fadd2_rn(py, zneg2(fy0));
+    const float* q0 = F + ((int)fy0.x * PITCH + (int)fx0.x);
+    const float* q1 = F + ((int)fy0.y * PITCH + (int)fx0.y);
+    const int dx0 = (fx1.x != fx0.x) ? 1 : 0, dy0 = (fy1.x != fy0.x) ? PITCH : 0;
+    const int dx1 = (fx1.y != fx0.y) ? 1 : 0, dy1 = (fy1.y != fy0.y) ? PITCH : 0;
+    const float2 f00 = make_float2(q0[0], q1[0]), f01 = make_float2(q0[dx0], q1[dx1]);
+    const float2 f10 = make_float2(q0[dy0], q1[dy1]), f11 = make_float2(q0[dy0 + dx0], q1[dy1 + dx1]);
+    const float2 t00 = __fmul2_rn(__fmul2_rn(ax, ay), f00), t01 = __fmul2_rn(__fmul2_rn(bx, ay), f01);
+    const float2 t10 = __fmul2_rn(__fmul2_rn(ax, by), f10), t11 = __fmul2_rn(__fmul2_rn(bx, by), f11);
+    float2 s = make_float2(t00.x + t01.x, t00.y + t01.y);
+    s.x = s.x + t10.x; s.y = s.y + t10.y;
+    s.x = s.x + t11.x; s.y = s.y + t11.y;
+    if (SCALE) s = __fmul2_rn(s, make_float2(scale, scale));
     return s;
 }
 
@@ -287,10 +366,11 @@ k_step_fused(const FusedArgs a)
                 const float4 va = zlds4(sv + i * FZ_PV + c0);
                 const float vr = sv[i * FZ_PV + c0 + 4];
                 float4 o;
-                o.x = (((ub.x - ua.x) + va.y) - va.x) / dt;
-                o.y = (((ub.y - ua.y) + va.z) - va.y) / dt;
-                o.z = (((ub.z - ua.z) + va.w) - va.z) / dt;
-                o.w = (((ub.w - ua.w) + vr) - va.w) / dt;
+                o.x = ((ub.x - ua.x) + va.y) - va.x;
+                o.y = ((ub.y - ua.y) + va.z) - va.y;
+                o.z = ((ub.z - ua.z) + va.w) - va.z;
+                o.w = ((ub.w - ua.w) + vr) - va.w;
+                o = zdiv4(o, dt);
                 if (!FULL) {
                     if (i >= h) o = zero4;
                     if (c0 + 0 >= w) o.x = 0.f;
@@ -369,23 +449,25 @@ k_step_fused(const FusedArgs a)
         FZ_TICK(4);
         // ---- a10/a11 advection (cyclic mapping): u by (u, v); v by (u', v); density by (u', v'), decay  :166-171
         {
-            float R[FZ_R][4];
+            // a thread's row of four cyclic cells is two pairs: columns (lane, lane + 32) and (lane + 64, lane + 96)
+            float2 R[FZ_R][2];
             float X = 0.f;
 #pragma unroll
             for (int r = 0; r < FZ_R; ++r)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = r0 + r, j = lane + 32 * k;
-                    R[r][k] = (FULL || (i <= h && j < w)) ? zadvect_cell<FZ_PU>(su, h + 1, w, su, sv, h, w, i, j, dt) : 0.f;
+                for (int kp = 0; kp < 2; ++kp) {
+                    const int i = r0 + r, j = lane + 64 * kp;
+                    R[r][kp] = zadvect_pair<FZ_PU, false>(su, h + 1, w, su, sv, h, w, i, j, dt, 1.0f);
                 }
             if (xu) X = zadvect_cell<FZ_PU>(su, h + 1, w, su, sv, h, w, 128, xe, dt);
             __syncthreads();
 #pragma unroll
             for (int r = 0; r < FZ_R; ++r)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = r0 + r, j = lane + 32 * k;
-                    if (FULL || (i <= h && j < w)) su[i * FZ_PU + j] = R[r][k];
+                for (int kp = 0; kp < 2; ++kp) {
+                    const int i = r0 + r, j = lane + 64 * kp;
+                    if (FULL || (i <= h && j < w)) su[i * FZ_PU + j] = R[r][kp].x;
+                    if (FULL || (i <= h && j + 32 < w)) su[i * FZ_PU + j + 32] = R[r][kp].y;
                 }
             if (xu) su[128 * FZ_PU + xe] = X;
             __syncthreads();
@@ -393,18 +475,19 @@ k_step_fused(const FusedArgs a)
 #pragma unroll
             for (int r = 0; r < FZ_R; ++r)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = r0 + r, j = lane + 32 * k;
-                    R[r][k] = (FULL || (i < h && j <= w)) ? zadvect_cell<FZ_PV>(sv, h, w + 1, su, sv, h, w, i, j, dt) : 0.f;
+                for (int kp = 0; kp < 2; ++kp) {
+                    const int i = r0 + r, j = lane + 64 * kp;
+                    R[r][kp] = zadvect_pair<FZ_PV, false>(sv, h, w + 1, su, sv, h, w, i, j, dt, 1.0f);
                 }
             if (xv) X = zadvect_cell<FZ_PV>(sv, h, w + 1, su, sv, h, w, xe, 128, dt);
             __syncthreads();
 #pragma unroll
             for (int r = 0; r < FZ_R; ++r)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = r0 + r, j = lane + 32 * k;
-                    if (FULL || (i < h && j <= w)) sv[i * FZ_PV + j] = R[r][k];
+                for (int kp = 0; kp < 2; ++kp) {
+                    const int i = r0 + r, j = lane + 64 * kp;
+                    if (FULL || (i < h && j <= w)) sv[i * FZ_PV + j] = R[r][kp].x;
+                    if (FULL || (i < h && j + 32 <= w)) sv[i * FZ_PV + j + 32] = R[r][kp].y;
                 }
             if (xv) sv[xe * FZ_PV + 128] = X;
             __syncthreads();
@@ -412,17 +495,18 @@ k_step_fused(const FusedArgs a)
 #pragma unroll
             for (int r = 0; r < FZ_R; ++r)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = r0 + r, j = lane + 32 * k;
-                    R[r][k] = (FULL || (i < h && j < w)) ? zadvect_cell<FZ_PD>(sd, h, w, su, sv, h, w, i, j, dt) * a.decay : 0.f;
+                for (int kp = 0; kp < 2; ++kp) {
+                    const int i = r0 + r, j = lane + 64 * kp;
+                    R[r][kp] = zadvect_pair<FZ_PD, true>(sd, h, w, su, sv, h, w, i, j, dt, a.decay);
                 }
             __syncthreads();
 #pragma unroll
             for (int r = 0; r < FZ_R; ++r)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = r0 + r, j = lane + 32 * k;
-                    if (FULL || (i < h && j < w)) sd[i * FZ_PD + j] = R[r][k];
+                for (int kp = 0; kp < 2; ++kp) {
+                    const int i = r0 + r, j = lane + 64 * kp;
+                    if (FULL || (i < h && j < w)) sd[i * FZ_PD + j] = R[r][kp].x;
+                    if (FULL || (i < h && j + 32 < w)) sd[i * FZ_PD + j + 32] = R[r][kp].y;
                 }
             __syncthreads();
         }

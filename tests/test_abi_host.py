@@ -102,3 +102,18 @@ def test_product_never_imports_the_oracle():
                     if re.search(r"\boracle\b", txt):
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_no_packed_fma_in_the_library():
+    """The arithmetic contract is 'every fp32 operation rounded once' (DESIGN.md s2).  ptxas 12.9 contracts
+    mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false; the kernels are written so that no packed add
+    consumes a packed product, and this test keeps it that way: no FFMA2 may appear anywhere in the SASS."""
+    import shutil
+    import subprocess
+    from smokephysai_b200 import _lib
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([tool, "-sass", _lib.SO_PATH], capture_output=True, text=True, check=True).stdout
+    assert "FADD2" in sass and "FMUL2" in sass, "expected the f32x2 kernels in the library"
+    assert "FFMA2" not in sass, "a packed multiply-add was contracted into FFMA2: results would not be rounded-once"

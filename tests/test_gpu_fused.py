@@ -151,3 +151,34 @@ def test_fused_c2_full_size_vs_oracle():
         assert_same(p[s], op[n_], "p seq %d" % s); assert_same(d[s], od[n_], "d seq %d" % s)
         assert_same(N(frames[s]), ofr[n_], "frames seq %d" % s)
     assert not d[:, -1, :].any() and not d[:, :, -1].any()
+
+
+@pytest.mark.parametrize("scale", [1e-44, 1e-41, 1e-38, 1e-33, 1e33])
+def test_fused_divergence_extreme_magnitudes(scale):
+    """The /dt of the divergence (navier_stokes.py:136) on denormal and huge numerators: the fused kernel routes those
+    warps through an fp64 division, which must round exactly like the IEEE fp32 division of the oracle / reference."""
+    h = w = 128
+    rng = np.random.default_rng(int(-np.log10(scale)) + 100)
+    st = {
+        "u": (rng.standard_normal((h + 1, w)) * scale).astype(np.float32),
+        "v": (rng.standard_normal((h, w + 1)) * scale).astype(np.float32),
+        "p": np.zeros((h, w), np.float32),
+        "density": np.zeros((h, w), np.float32),
+    }
+    # a patch of ordinary values so that warps mix ordinary and extreme lanes
+    st["u"][40:60, 30:90] = rng.standard_normal((20, 60)).astype(np.float32)
+    ref = oracle.OracleSolver((h, w), 0.01, 0.001, 3)
+    fz = make(h, w, K=3, step_kernel="fused")
+    ph = make(h, w, K=3, step_kernel="phases")
+    for k in FIELDS:
+        setattr(ref, k, st[k].copy())
+        setattr(fz, k, T(st[k]))
+        setattr(ph, k, T(st[k]))
+    for t in range(2):
+        ref.step()
+        fz.step()
+        ph.step()
+        for k in FIELDS:
+            a, b, c = N(getattr(fz, k)), getattr(ref, k), N(getattr(ph, k))
+            assert np.array_equal(a, b, equal_nan=True), "scale %g step %d %s fused vs oracle" % (scale, t, k)
+            assert np.array_equal(c, b, equal_nan=True), "scale %g step %d %s phases vs oracle" % (scale, t, k)
