@@ -267,7 +267,9 @@ k_step_fused(const FusedArgs a)
 
     // frame output of the step just finished (:173, fractal_generator.py:62) and buoyancy of the next one
     // (:154-155: v[:, :-1] += dt * (density * 0.1)); both read the thread's own strip of density.
-    auto frame_and_buoyancy = [&](float* frame, const bool buoy) {
+    // (mrow: the thread's eight float4 of the fractal multiplier, loaded by the caller ahead of time so that the L2
+    // latency hides behind the density write-back and its barriers)
+    auto frame_and_buoyancy = [&](float* frame, const bool buoy, const float4 (&mrow)[FZ_R]) {
 #pragma unroll
         for (int r = 0; r < FZ_R; ++r) {
             const int i = r0 + r;
@@ -276,7 +278,7 @@ k_step_fused(const FusedArgs a)
                 if (frame) {
                     float4 fr = d4;
                     if (a.fmul) {
-                        const float4 m = __ldg(reinterpret_cast<const float4*>(a.fmul + (size_t)i * pc + c0));
+                        const float4 m = mrow[r];
                         fr.x = fr.x + m.x * fr.x; fr.y = fr.y + m.y * fr.y; fr.z = fr.z + m.z * fr.z; fr.w = fr.w + m.w * fr.w;
                     }
                     *reinterpret_cast<float4*>(frame + (size_t)i * pc + c0) = fr;
@@ -293,7 +295,10 @@ k_step_fused(const FusedArgs a)
         }
     };
 
-    if (a.nsteps > 0) frame_and_buoyancy(nullptr, true);
+    {
+        const float4 none[FZ_R] = {};
+        if (a.nsteps > 0) frame_and_buoyancy(nullptr, true, none);
+    }
     __syncthreads();
     FZ_TICK(0);
 
@@ -447,6 +452,7 @@ k_step_fused(const FusedArgs a)
         __syncthreads();
 
         FZ_TICK(4);
+        float4 mrow[FZ_R] = {};
         // ---- a10/a11 advection (cyclic mapping): u by (u, v); v by (u', v); density by (u', v'), decay  :166-171
         {
             // a thread's row of four cyclic cells is two pairs: columns (lane, lane + 32) and (lane + 64, lane + 96)
@@ -500,6 +506,13 @@ k_step_fused(const FusedArgs a)
                     R[r][kp] = zadvect_pair<FZ_PD, true>(sd, h, w, su, sv, h, w, i, j, dt, a.decay);
                 }
             __syncthreads();
+            if (a.frames && a.fmul) {
+#pragma unroll
+                for (int r = 0; r < FZ_R; ++r) {
+                    const int i = r0 + r;
+                    if (FULL || (i < h && colin)) mrow[r] = __ldg(reinterpret_cast<const float4*>(a.fmul + (size_t)i * pc + c0));
+                }
+            }
 #pragma unroll
             for (int r = 0; r < FZ_R; ++r)
 #pragma unroll
@@ -514,7 +527,7 @@ k_step_fused(const FusedArgs a)
         FZ_TICK(5);
         // ---- a11 returned copy of this step + buoyancy of the next
         float* frame = a.frames ? a.frames + b * a.frame_batch_stride + (size_t)t * a.frame_step_stride : nullptr;
-        frame_and_buoyancy(frame, t + 1 < a.nsteps);
+        frame_and_buoyancy(frame, t + 1 < a.nsteps, mrow);
         __syncthreads();
         FZ_TICK(6);
     }
