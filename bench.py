@@ -302,7 +302,9 @@ def main():
         working_set = ns._arena.numel() * 4 + frames.numel() * 4
         emitter_lists = [[((x, y), i) for x, y, _, i in lst] for lst in ems]
 
-        def device_step():
+        replayed = [0, 0]
+
+        def device_step(eager=False):
             ns.setup_grid()
             ns.splat_uploaded(src, off)
             ns.run_steps(T, fmul=fmul, out=frames)
@@ -316,7 +318,7 @@ def main():
         total_cells_per_step = world * cells_per_step_rank
         parallelism = "sequences sharded over %d GPU(s), no data-path collective" % world
     else:
-        from smokephysai_b200.slab import SlabNavierStokes
+        from smokephysai_b200.slab import SlabNavierStokes, sweep_split
         Tj = args.sweeps_per_launch or 10
         slab = SlabNavierStokes((h, w), 0.01, 0.001, dev, rank=rank, world=world, jacobi_iters=K, sweeps_per_launch=Tj)
         ems = emitters_for_sequence(0, h, w)
@@ -327,9 +329,30 @@ def main():
         h2d_bytes = 16 * len(ems) + 8
         host_d = torch.empty(slab.geom.R1 - slab.geom.R0, w, dtype=torch.float32).pin_memory()
 
-        def device_step():
-            for _ in range(T):
-                slab.step()
+        slab.step()                                   # eager once: NCCL sets up its P2P connections on first use
+        graph_note = "eager launches"
+        graph = None
+        replayed = [0, 0]                             # [graph replays, library launches recorded in the graph]
+        if os.environ.get("SMK_BENCH_GRAPH", "0") == "1":   # opt-in: capturing NCCL P2P hung on this stack
+            try:
+                n_cap = 1 if len(sweep_split(K, Tj)) % 2 == 0 else 2
+                if T % n_cap == 0:
+                    c0 = _lib.launch_count()
+                    graph = slab.capture(n_cap)
+                    replayed[1] = _lib.launch_count() - c0
+                    graph_note = "CUDA graph of %d step(s) (kernels + NCCL send/recv), replayed" % n_cap
+            except Exception as e:                    # capture is an optimisation of the host path only
+                graph = None
+                graph_note = "eager launches (graph capture failed: %s)" % repr(e)[:120]
+
+        def device_step(eager=False):
+            if graph is not None and not eager:
+                for _ in range(T // n_cap):
+                    graph.replay()
+                replayed[0] += T // n_cap
+            else:
+                for _ in range(T):
+                    slab.step()
 
         def e2e_step():
             slab.setup_grid()
@@ -345,7 +368,7 @@ def main():
         scaling = "strong"
         total_cells_per_step = h * w * T
         parallelism = ("row slabs over %d GPU(s), halo %d rows, NCCL send/recv of p after every launch of <= %d fused sweeps "
-                       "and of u,v,density once per step" % (world, slab.halo, Tj)) if world > 1 else "single GPU, undecomposed"
+                       "and of u,v,density once per step; %s" % (world, slab.halo, Tj, graph_note)) if world > 1 else "single GPU, undecomposed; " + graph_note
 
     # ---- device-resident throughput -----------------------------------------------------------------
     for _ in range(args.warmup):
@@ -355,6 +378,7 @@ def main():
     if rank == 0:
         clocks.start()
     n0 = _lib.launch_count()
+    r0 = replayed[0]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -363,7 +387,7 @@ def main():
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.launch_count() - n0
+    launches = _lib.launch_count() - n0 + (replayed[0] - r0) * replayed[1]      # kernels inside replayed graphs count too
     clk = clocks.stop() if rank == 0 else None
     value = total_cells_per_step * args.steps / (ms * 1e-3)
 
@@ -371,7 +395,7 @@ def main():
     barrier()
     _lib.profile_begin(max_records=launches + 64)
     for _ in range(args.steps):
-        device_step()
+        device_step(eager=True)          # per-launch events cannot be recorded inside a replayed graph
     torch.cuda.synchronize()
     prof = _lib.profile_end()
 

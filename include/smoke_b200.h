@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMK_ABI_VERSION 3
+#define SMK_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define SMK_API __attribute__((visibility("default")))
@@ -208,6 +208,26 @@ SMK_API int smk_frame_features(const float* frames, int64_t frame_stride, int32_
 /*   sumsq[n] = ||frame[n+1] - frame[n]||^2 (double), n < nframes-1: the distances of compute_lyapunov_exponent (:67-87) */
 SMK_API int smk_frame_distances(const float* frames, int64_t frame_stride, int32_t nframes, int32_t h, int32_t w,
                         int32_t pitch, double* sumsq, void* stream);
+
+/* ---- slab halo exchange over NCCL, driven from C (rows are contiguous, one send and one receive
+ *      of rows x pitch floats per neighbour and field) -----------------------------------------------------
+ * The library does not link NCCL: smk_nccl_load finds the libnccl.so.2 already in the process (PyTorch's) or at
+ * libpath_host; without it these entry points return SMK_EUNSUPPORTED.  Typical use: every rank calls
+ * smk_nccl_load; rank 0 calls smk_nccl_unique_id and broadcasts the 128 bytes over the host's own channel
+ * (torch.distributed); every rank calls smk_nccl_comm_init (collective, blocks until all ranks arrive); then one
+ * smk_nccl_exchange per exchange phase of the step: all blocks of the call form one ncclGroup on `stream`.
+ * NCCL errors are returned as 1000 + ncclResult_t. */
+typedef struct smk_halo_block {
+    void* ptr;          /* device pointer of the first element of the block                          */
+    int64_t count;      /* fp32 elements (rows x pitch)                                              */
+    int32_t peer;       /* rank of the neighbour                                                     */
+    int32_t is_send;    /* 1: ncclSend, 0: ncclRecv                                                  */
+} smk_halo_block_t;
+SMK_API int smk_nccl_load(const char* libpath_host, int32_t* version_host);
+SMK_API int smk_nccl_unique_id(void* id128_host);
+SMK_API int smk_nccl_comm_init(const void* id128_host, int32_t rank, int32_t world, void** comm_out_host);
+SMK_API int smk_nccl_comm_destroy(void* comm);
+SMK_API int smk_nccl_exchange(void* comm, const smk_halo_block_t* blocks_host, int32_t nblocks, void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,10 @@ class Params(C.Structure):                   # smk_params_t
 STEP_KERNELS = {"auto": 0, "phases": 1, "fused": 2}           # SMK_STEP_AUTO / _PHASES / _FUSED
 
 
+class HaloBlock(C.Structure):                # smk_halo_block_t
+    _fields_ = [("ptr", c_p), ("count", c_i64), ("peer", c_i32), ("is_send", c_i32)]
+
+
 GP, SP, PP = C.POINTER(Grid), C.POINTER(State), C.POINTER(Params)
 
 # name -> argtypes; every function returns int except smk_last_error_string.  Kept in one table so
@@ -68,6 +72,11 @@ SIGNATURES = {
     "smk_frame_features": [c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_f, c_f, c_p, c_p, c_p, c_p],
     "smk_frame_distances": [c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
     "smk_apply_mul": [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i64, c_p],
+    "smk_nccl_load": [C.c_char_p, C.POINTER(c_i32)],
+    "smk_nccl_unique_id": [c_p],
+    "smk_nccl_comm_init": [c_p, c_i32, c_i32, C.POINTER(c_p)],
+    "smk_nccl_comm_destroy": [c_p],
+    "smk_nccl_exchange": [c_p, C.POINTER(HaloBlock), c_i32, c_p],
 }
 
 _lib = None

@@ -13,14 +13,14 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libsmoke_sm100.so")
-SOURCES = ["abi.cu", "jacobi.cu", "stencil.cu", "features.cu", "fused.cu"]
+SOURCES = ["abi.cu", "jacobi.cu", "stencil.cu", "features.cu", "fused.cu", "nccl_halo.cu"]
 HEADERS = ["common.cuh", "jacobi_core.cuh", os.path.join("..", "..", "include", "smoke_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
-    "-cudart", "static",
+    "-cudart", "static", "-ldl",
 ]
 
 

@@ -22,8 +22,9 @@ Only the advection needs to know where the slab sits (absolute fp32 coordinates,
 smk_grid_t.row0 / gh); all other kernels run on the slab as if it were a small grid, because a slab edge
 that is not a grid edge only produces garbage in ghost rows that are already written off.
 
-Exchangers: `DistExchanger` (torch.distributed P2P: NCCL over NVLink on GPUs, gloo in the CPU tests) and
-`LocalGroup` (all slabs in one process on one GPU: the way to test the decomposition without a multi-GPU box).
+Exchangers: `NcclExchanger` (the default on GPUs: the library's own NCCL communicator, one C call per exchange
+phase: ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd over NVLink), `DistExchanger` (torch.distributed P2P ops:
+gloo in the CPU tests, NCCL if asked for) and `LocalGroup` (all slabs in one process on one GPU: the way to test the decomposition without a multi-GPU box).
 """
 import ctypes as C
 
@@ -125,6 +126,69 @@ class DistExchanger:
                 req.wait()
 
 
+class NcclExchanger:
+    """Halo exchange through the library's own NCCL communicator (include/smoke_b200.h: smk_nccl_*): all sends and
+    receives of an exchange phase are one ncclGroup issued by ONE C call on the current stream.  The same traffic
+    through torch.distributed's P2P ops costs ~25 us of host time per op (~250 us per step for the three phases),
+    which bound the 8-GPU step (tools/slab_host_time.py).  The 128-byte NCCL id travels over the existing
+    torch.distributed group; construction is collective (every rank of the group must build one)."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed as dist
+        self.device = torch.device(device)
+        ver = C.c_int32(0)
+        _lib.call("smk_nccl_load", None, C.byref(ver))
+        self.nccl_version = ver.value
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        on_gpu = dist.get_backend(group) == "nccl"
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            _lib.call("smk_nccl_unique_id", idbuf.data_ptr())
+        t = idbuf.to(self.device) if on_gpu else idbuf
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        idbuf = t.cpu().contiguous()
+        self.comm = C.c_void_p()
+        _lib.call("smk_set_device", self.device.index)
+        _lib.call("smk_nccl_comm_init", idbuf.data_ptr(), self.rank, self.world, C.byref(self.comm))
+        self._plans = {}
+
+    def _plan(self, geom, tensors):
+        key = tuple((t.data_ptr(), kind) for t, kind in tensors)
+        plan = self._plans.get(key)
+        if plan is None:
+            blocks = []
+            for t, kind in tensors:
+                if not t.is_contiguous() or t.dtype != torch.float32:
+                    raise ValueError("halo exchange needs contiguous fp32 [rows, pitch] tensors")
+                pitch = t.shape[1]
+                sends, recvs = geom.blocks(kind)
+                for peer, a, n in recvs:
+                    blocks.append(_lib.HaloBlock(t.data_ptr() + 4 * a * pitch, n * pitch, peer, 0))
+                for peer, a, n in sends:
+                    blocks.append(_lib.HaloBlock(t.data_ptr() + 4 * a * pitch, n * pitch, peer, 1))
+            plan = ((_lib.HaloBlock * max(len(blocks), 1))(*blocks), len(blocks))
+            self._plans[key] = plan
+        return plan
+
+    def exchange(self, geom, tensors):
+        arr, n = self._plan(geom, tensors)
+        _lib.call("smk_nccl_exchange", self.comm, arr, n, torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "comm", None) is not None and self.comm:
+            torch.cuda.synchronize(self.device)
+            _lib.call("smk_nccl_comm_destroy", self.comm)
+            self.comm = None
+
+
+def default_exchanger(device):
+    """NcclExchanger when the default process group runs NCCL on GPUs, else torch.distributed P2P (gloo on CPU)."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_backend() == "nccl" and torch.device(device).type == "cuda":
+        return NcclExchanger(device)
+    return DistExchanger()
+
+
 def local_exchange(geoms, tensor_lists):
     """In-process exchange between all slabs: tensor_lists[r] = list of (tensor, kind) of rank r."""
     for r, geom in enumerate(geoms):
@@ -154,7 +218,7 @@ class SlabNavierStokes:
         self.rank, self.world = int(rank), int(world)
         self.local = NavierStokesSimulator((self.geom.hl, W), dt, viscosity, device, jacobi_iters=jacobi_iters,
                                            sweeps_per_launch=self.T, _slab=(self.geom.A, H))
-        self.exchanger = exchanger if exchanger is not None else (DistExchanger() if world > 1 else None)
+        self.exchanger = exchanger if exchanger is not None else (default_exchanger(self.local._cuda) if world > 1 else None)
         self._overflow = torch.zeros(1, dtype=torch.int32, device=self.local._cuda)
         self.steps_done = 0
 
@@ -264,6 +328,27 @@ class SlabNavierStokes:
                 self.exchanger.exchange(self.geom, self.exchange_list(arg))
             else:
                 arg()
+
+    def capture(self, nsteps=1):
+        """Record `nsteps` consecutive steps -- kernels and NCCL halo exchanges -- into a CUDA graph and return it
+        (`graph.replay()` then advances the slab by nsteps; all ranks must replay together).  At eight slabs the
+        step is a few hundred microseconds of kernels, less than what Python and the NCCL host path spend
+        enqueueing its ~10 launches and 3 grouped send/recvs; a replayed graph removes that host time.  One eager
+        step must have run before (NCCL builds its P2P connections on first use, which cannot be captured), and
+        the ping-pong state has to come back to the same buffers after nsteps (it does after every step when the
+        number of Jacobi launches per step is even, else after every second step)."""
+        ns = self.local
+        st = ns._state
+        before = (st.cur_u, st.cur_v, st.cur_d, st.cur_p)
+        torch.cuda.synchronize(ns._cuda)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(int(nsteps)):
+                self.step()
+        after = (st.cur_u, st.cur_v, st.cur_d, st.cur_p)
+        if after != before:
+            raise RuntimeError("the ping-pong state does not return to the same buffers after %d step(s): capture an even number" % nsteps)
+        return graph
 
     def check(self):
         """Raise if an advection back-trace ever left the rows this slab holds exactly (synchronises)."""

@@ -46,7 +46,7 @@ def test_ctypes_table_matches_header(so_path):
     for name, args in table.items():
         assert len(args) == decl[name], "%s: %d ctypes args vs %d in the header" % (name, len(args), decl[name])
     lib = _lib.load()
-    assert lib.smk_version() == 3
+    assert lib.smk_version() == 4
     assert isinstance(lib.smk_last_error_string(), bytes)
 
 

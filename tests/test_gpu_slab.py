@@ -86,7 +86,7 @@ def test_single_rank_slab_is_the_plain_solver():
 
 
 # --------------------------------------------------------------------------- real NCCL, needs >= 2 GPUs
-def _nccl_worker(rank, world, port, H, W, K, T, steps, out_dir):
+def _nccl_worker(rank, world, port, H, W, K, T, steps, out_dir, exch):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -94,7 +94,10 @@ def _nccl_worker(rank, world, port, H, W, K, T, steps, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         st0 = random_state(H, W, seed=21)
-        slab = SlabNavierStokes((H, W), 0.02, 0.01, "cuda:%d" % rank, rank=rank, world=world, jacobi_iters=K, sweeps_per_launch=T)
+        from smokephysai_b200.slab import DistExchanger, NcclExchanger
+        slab = SlabNavierStokes((H, W), 0.02, 0.01, "cuda:%d" % rank, rank=rank, world=world, jacobi_iters=K, sweeps_per_launch=T,
+                                exchanger=DistExchanger() if exch == "torch" else None)
+        assert isinstance(slab.exchanger, DistExchanger if exch == "torch" else NcclExchanger)
         for k in ("u", "v", "p", "d"):
             slab.scatter(k, st0[k])
         for _ in range(steps):
@@ -109,14 +112,17 @@ def _nccl_worker(rank, world, port, H, W, K, T, steps, out_dir):
 
 
 @pytest.mark.timeout(300)
-def test_nccl_slabs_match_undecomposed(tmp_path):
+@pytest.mark.parametrize("exch", ["library", "torch"])
+def test_nccl_slabs_match_undecomposed(tmp_path, exch):
+    """Real NCCL over NVLink: halo exchange through the library's own communicator (smk_nccl_exchange, the default) and
+    through torch.distributed P2P ops; both must reproduce the undecomposed run bit for bit."""
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     import torch.multiprocessing as mp
     H, W, K, T, steps = 512, 384, 20, 10, 3
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_nccl_worker, args=(world, port, H, W, K, T, steps, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, port, H, W, K, T, steps, str(tmp_path), exch), nprocs=world, join=True)
     st0 = random_state(H, W, seed=21)
     whole = NavierStokesSimulator((H, W), 0.02, 0.01, "cuda", jacobi_iters=K)
     for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
