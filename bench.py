@@ -251,6 +251,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweeps-per-launch", type=int, default=0)
+    ap.add_argument("--halo", type=int, default=0, help="c4: ghost rows per slab side (0: K + 4, one halo exchange per step; "
+                    "sweeps-per-launch + 4 is the minimum and exchanges p after every Jacobi launch)")
     ap.add_argument("--step-kernel", default="auto", choices=["auto", "phases", "fused"],
                     help="auto: whole simulation on one SM for grids <= 128x128 (k_step_fused), else one kernel per phase")
     args = ap.parse_args()
@@ -320,7 +322,8 @@ def main():
     else:
         from smokephysai_b200.slab import SlabNavierStokes, sweep_split
         Tj = args.sweeps_per_launch or 10
-        slab = SlabNavierStokes((h, w), 0.01, 0.001, dev, rank=rank, world=world, jacobi_iters=K, sweeps_per_launch=Tj)
+        slab = SlabNavierStokes((h, w), 0.01, 0.001, dev, rank=rank, world=world, jacobi_iters=K, sweeps_per_launch=Tj,
+                                halo=args.halo or (K + 4 if world > 1 else None))
         ems = emitters_for_sequence(0, h, w)
         slab.add_sources(ems)
         cells_per_step_rank = (slab.geom.R1 - slab.geom.R0) * w * T
@@ -367,8 +370,14 @@ def main():
         e2e_api = "SlabNavierStokes: setup_grid + add_sources(host list) + %d x step() + owned density rows -> pinned host" % T
         scaling = "strong"
         total_cells_per_step = h * w * T
-        parallelism = ("row slabs over %d GPU(s), halo %d rows, NCCL send/recv of p after every launch of <= %d fused sweeps "
-                       "and of u,v,density once per step; %s" % (world, slab.halo, Tj, graph_note)) if world > 1 else "single GPU, undecomposed; " + graph_note
+        if world == 1:
+            parallelism = "single GPU, undecomposed; " + graph_note
+        elif slab.single_exchange:
+            parallelism = ("row slabs over %d GPU(s), halo %d rows (>= K + 4): ONE NCCL send/recv group per step (u, v, density, p), "
+                           "issued from C (smk_nccl_exchange); %s" % (world, slab.halo, graph_note))
+        else:
+            parallelism = ("row slabs over %d GPU(s), halo %d rows, NCCL send/recv (smk_nccl_exchange) of p after every launch of <= %d "
+                           "fused sweeps and of u,v,density once per step; %s" % (world, slab.halo, Tj, graph_note))
 
     # ---- device-resident throughput -----------------------------------------------------------------
     for _ in range(args.warmup):

@@ -271,10 +271,10 @@ int launch_jacobi(const smk_grid_t* g, const float* div, float* p, float* scratc
     int tile = 0;                                   // 0 auto, 1: 64 x 128 (8 warps), 2: 128 x 128 (16 warps), 3: 64 x 128 (16 warps)
     if (const char* e = getenv("SMK_JACOBI_TILE")) tile = atoi(e);
     if (tile == 0) {
-        // Many waves of CTAs (>= 4096^2): 64 x 128 tiles at two CTAs per SM, so that one CTA's tile load / store overlaps
+        // Many waves of CTAs (>= 4 per SM: 4096^2, or a 1/8 slab of 8192^2): 64 x 128 tiles at two CTAs per SM, so that one CTA's tile load / store overlaps
         // the other's sweeps: 7-8 % faster than 128 x 128 tiles at 4096^2 and 8192^2, equal at 2048^2 (tools/tune_jacobi.py).
         const long ctas128 = (long)ntiles(g->w, 128, 12) * ntiles(g->h, 128, 10) * g->batch;
-        if (ctas128 >= 6L * sm_count()) tile = 1;
+        if (ctas128 >= 4L * sm_count()) tile = 1;
     }
     if (T <= 0) T = (tile == 1 || tile == 3) ? 10 : pick_T(g, K, 128, 24, sm_count());
     if (tile == 1) return run_cfg<8, 8>(g, div, p, scratch, K, min(T, 12), in_scratch, s);

@@ -18,6 +18,10 @@ one send and one receive of `rows x pitch` floats per neighbour and field) refre
 
 so halo >= T + 4 rows keeps every owned row exact as long as the back-trace reaches at most halo - 4 rows;
 the advect kernel checks that on the device (smk_slab_check_t) and `check()` raises if it was violated.
+With a halo of at least K + 4 rows (K = jacobi_iters) the p ghosts survive all K sweeps of a step, and the plan
+collapses to ONE exchange per step -- u, v, density and p in a single NCCL group -- at the price of K + 4 instead
+of T + 4 redundant rows per side: at 8 slabs of 8192^2 that trades 2 x 14 -> 2 x 24 ghost rows (of 1024) for two
+fewer latency-bound exchange phases per step (`halo=` picks; bench.py --halo).
 Only the advection needs to know where the slab sits (absolute fp32 coordinates, global edge tests:
 smk_grid_t.row0 / gh); all other kernels run on the slab as if it were a small grid, because a slab edge
 that is not a grid edge only produces garbage in ghost rows that are already written off.
@@ -212,6 +216,8 @@ class SlabNavierStokes:
         self.halo = int(halo) if halo is not None else self.T + 4
         if world > 1 and self.halo < self.T + 3:
             raise ValueError("halo of %d rows is too shallow for %d fused sweeps per launch (need >= T + 3)" % (self.halo, self.T))
+        # deep halo: the pressure ghosts stay exact through all K sweeps, one exchange per step (u, v, density, p)
+        self.single_exchange = world > 1 and self.halo >= int(jacobi_iters) + 4
         self.geom = SlabGeometry(H, W, world, rank, self.halo if world > 1 else 0)
         self.grid_size, self.dt, self.viscosity = (H, W), dt, viscosity
         self.jacobi_iters = int(jacobi_iters)
@@ -284,8 +290,11 @@ class SlabNavierStokes:
         g = self.geom
         if self.world == 1:
             return None
-        lo = 0 if g.top_edge else 2
-        hi = rows if g.bottom_edge else rows - 2
+        # rows of the advected field / velocities that are no longer exact next to a cut: 2 when p was refreshed
+        # just before the gradient subtract, K + 2 when the step's only exchange was at its start
+        m = self.jacobi_iters + 2 if self.single_exchange else 2
+        lo = 0 if g.top_edge else m
+        hi = rows if g.bottom_edge else rows - m
         return SlabCheck(g.own_lo, min(g.own_hi + 1, rows), lo, hi, self._overflow.data_ptr())
 
     def _project_advect(self):
@@ -309,11 +318,11 @@ class SlabNavierStokes:
         """The step as a list of ("x", field names) halo exchanges and ("c", callable) compute phases."""
         plan = []
         if self.world > 1:
-            plan.append(("x", ("u", "v", "d")))
+            plan.append(("x", ("u", "v", "d", "p") if self.single_exchange else ("u", "v", "d")))
         plan.append(("c", self._fdd))
         for t in sweep_split(self.jacobi_iters, self.T):
             plan.append(("c", (lambda t=t: self._jacobi(t))))
-            if self.world > 1:
+            if self.world > 1 and not self.single_exchange:
                 plan.append(("x", ("p",)))
         plan.append(("c", self._project_advect))
         return plan
@@ -353,8 +362,9 @@ class SlabNavierStokes:
     def check(self):
         """Raise if an advection back-trace ever left the rows this slab holds exactly (synchronises)."""
         if int(self._overflow.item()) != 0:
+            reach = self.halo - (self.jacobi_iters + 4 if self.single_exchange else 4)
             raise RuntimeError("slab halo of %d rows is too shallow for the velocities reached (|dt*v| > %d rows): "
-                               "results near the slab boundary are not exact; use a deeper halo" % (self.halo, self.halo - 4))
+                               "results near the slab boundary are not exact; use a deeper halo" % (self.halo, reach))
 
     def gather(self, name):
         """All ranks: the global field assembled from every rank's owned rows (torch.distributed all_gather)."""

@@ -22,12 +22,18 @@ def N(t):
     return t.detach().cpu().numpy()
 
 
-@pytest.mark.parametrize("world,K,T,H,W", [(2, 20, 10, 96, 40), (3, 13, 4, 90, 133), (4, 24, 8, 300, 260), (8, 20, 10, 1024, 512)])
-def test_local_group_matches_undecomposed(world, K, T, H, W):
+@pytest.mark.parametrize("world,K,T,H,W,halo", [
+    (2, 20, 10, 96, 40, None), (3, 13, 4, 90, 133, None), (4, 24, 8, 300, 260, None), (8, 20, 10, 1024, 512, None),
+    # deep halos (>= K + 4): one exchange per step, u, v, density and p together
+    (2, 20, 10, 96, 40, 28), (3, 9, 4, 150, 133, 14), (8, 20, 10, 1024, 512, 26),
+])
+def test_local_group_matches_undecomposed(world, K, T, H, W, halo):
     dt, nu, steps = 0.02, 0.01, 3
     st0 = random_state(H, W, seed=world * 7 + K)
     whole = NavierStokesSimulator((H, W), dt, nu, "cuda", jacobi_iters=K)
-    grp = LocalGroup((H, W), dt, nu, "cuda", world=world, jacobi_iters=K, sweeps_per_launch=T)
+    grp = LocalGroup((H, W), dt, nu, "cuda", world=world, jacobi_iters=K, sweeps_per_launch=T, halo=halo)
+    assert all(s.single_exchange == (halo is not None) for s in grp.slabs)
+    assert sum(1 for kind, _ in grp.slabs[0].step_plan() if kind == "x") == (1 if halo is not None else 1 + len(range(0, K, T)))
     for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
         setattr(whole, name, torch.from_numpy(st0[k]).cuda())
         grp.scatter(k, st0[k])

@@ -13,13 +13,16 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-slab = SlabNavierStokes((n, n), 0.01, 0.001, torch.device("cuda", local), rank=rank, world=world, jacobi_iters=20, sweeps_per_launch=10)
+halo = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+slab = SlabNavierStokes((n, n), 0.01, 0.001, torch.device("cuda", local), rank=rank, world=world, jacobi_iters=20, sweeps_per_launch=10,
+                        halo=halo or None)
 slab.add_sources([(n // 2, n // 2, 8, 1.5)])
 for _ in range(5):
     slab.step()
 torch.cuda.synchronize()
 dist.barrier()
 for label, fn in (("whole step", slab.step),
+                  ("exchange(u,v,d,p) only", lambda: slab.exchanger.exchange(slab.geom, slab.exchange_list(("u", "v", "d", "p")))),
                   ("exchange(u,v,d) only", lambda: slab.exchanger.exchange(slab.geom, slab.exchange_list(("u", "v", "d")))),
                   ("exchange(p) only", lambda: slab.exchanger.exchange(slab.geom, slab.exchange_list(("p",)))),
                   ("compute phases only", lambda: [arg() for kind, arg in slab.step_plan() if kind == "c"])):
