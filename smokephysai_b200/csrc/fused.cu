@@ -556,10 +556,24 @@ k_step_fused(const FusedArgs a)
     FZ_TICK(7);
 }
 
+// does the current device give one CTA the 226.5 KB the fused kernel needs (B200: 227 KB)?
+static bool device_has_room()
+{
+    static int ok[64] = {};                 // 0 unknown, 1 yes, -1 no
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    if (ok[dev] == 0) {
+        int optin = 0;
+        ok[dev] = (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess &&
+                   (size_t)optin >= FZ_SMEM) ? 1 : -1;
+    }
+    return ok[dev] == 1;
+}
+
 bool fused_supported(const smk_grid_t* g)
 {
     return g->h >= 2 && g->w >= 2 && g->h <= 128 && g->w <= 128 && g->pitch_u <= FZ_PU && g->pitch_v <= FZ_PV && g->pitch_c <= FZ_PD &&
-           (g->gh == 0 || (g->gh == g->h && g->row0 == 0));
+           (g->gh == 0 || (g->gh == g->h && g->row0 == 0)) && device_has_room();
 }
 
 int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float* p, int nsteps, float* frames,
@@ -569,12 +583,15 @@ int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float*
     if (!fused_supported(g)) return fail(SMK_EUNSUPPORTED, "k_step_fused: needs a non-slab grid of at most 128 x 128 cells, got %d x %d", g->h, g->w);
     if (nsteps <= 0) return SMK_OK;
     const bool full = g->h == 128 && g->w == 128 && g->pitch_u == 128 && g->pitch_v == 132 && g->pitch_c == 128;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+    static bool attr_set[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 63;
+    if (!attr_set[dev] || dev == 63) {
         cudaError_t e = cudaFuncSetAttribute(k_step_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM);
         if (e != cudaSuccess) return fail((int)e, "k_step_fused: cannot opt in to %zu B of shared memory: %s", FZ_SMEM, cudaGetErrorString(e));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     FusedArgs a;
     a.U = u; a.V = v; a.D = d; a.P = p; a.frames = frames; a.fmul = fmul;
