@@ -464,7 +464,7 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "grid": [h, w], "sequences_per_gpu": B, "jacobi_iters": K, "time_steps_per_bench_step": T,
-                   "parallelism": parallelism, "step_kernel": ("fused" if (not slab_mode and ns.step_is_fused()) else "phases"),
+                   "parallelism": parallelism, "step_kernel": ("fused" if (not slab_mode and ns.step_is_fused(T)) else "phases"),
                    "l2": "no flush: working set %.0f MB per GPU (fields + frames) > 126 MB L2" % (working_set / 1e6)},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

@@ -99,7 +99,8 @@ typedef struct smk_params {
  *   SMK_STEP_FUSED   the whole simulation on one SM -- u, v, density in shared memory, pressure in registers --
  *                    for all the steps of the call in a single launch; grids of at most 128 x 128 cells only
  *                    (SMK_EUNSUPPORTED otherwise)
- *   SMK_STEP_AUTO    fused when the grid qualifies, else phases                                   */
+ *   SMK_STEP_AUTO    fused when the grid qualifies and the call carries enough work for one-simulation-per-SM
+ *                    execution to win: two or more steps per call, or one step of at least 32 simulations */
 enum { SMK_STEP_AUTO = 0, SMK_STEP_PHASES = 1, SMK_STEP_FUSED = 2 };
 
 SMK_API int smk_version(void);
@@ -174,8 +175,8 @@ SMK_API int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* p
 SMK_API int smk_run_steps(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, int32_t nsteps,
                   float* frames, int64_t frame_step_stride, int64_t frame_batch_stride,
                   const float* fmul, void* stream);
-/*     1 when smk_step / smk_run_steps would take the fused single-launch path for this grid and params */
-SMK_API int smk_step_is_fused(const smk_grid_t* g, const smk_params_t* prm, int32_t* fused_host);
+/*     1 when a call of nsteps steps (smk_step: 1) would take the fused single-launch path for this grid and params */
+SMK_API int smk_step_is_fused(const smk_grid_t* g, const smk_params_t* prm, int32_t nsteps, int32_t* fused_host);
 
 /* diagnostics: per simulation {max|div|, sum div^2} of the un-normalised divergence of (u, v);
  *     out[2*batch] must be zeroed by the caller; warp-shuffle + atomic reduction. */

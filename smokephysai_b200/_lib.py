@@ -66,7 +66,7 @@ SIGNATURES = {
     "smk_advect_slab": [GP, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_f, c_f, C.POINTER(SlabCheck), c_p],
     "smk_step": [GP, SP, PP, c_p, c_i64, c_p, c_p],
     "smk_run_steps": [GP, SP, PP, c_i32, c_p, c_i64, c_i64, c_p, c_p],
-    "smk_step_is_fused": [GP, PP, C.POINTER(c_i32)],
+    "smk_step_is_fused": [GP, PP, c_i32, C.POINTER(c_i32)],
     "smk_div_norms": [GP, c_p, c_p, c_p, c_p],
     "smk_fractal_fields": [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f, c_i32, c_p, c_p, c_p, c_p, c_p],
     "smk_frame_features": [c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_f, c_f, c_p, c_p, c_p, c_p],

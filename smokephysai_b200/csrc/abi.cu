@@ -247,24 +247,31 @@ int smk_advect_slab(const smk_grid_t* g, const float* field, float* out, int32_t
     return launch_advect(g, field, out, rows, cols, pitch, 0, u, v, dt, scale, nullptr, 0, nullptr, chk, (cudaStream_t)stream);
 }
 
-static int pick_step_kernel(const smk_grid_t* g, const smk_params_t* prm, int* fused)
+// SMK_STEP_AUTO: the fused kernel runs one simulation per SM, so it pays off when a call carries enough work per
+// launch -- several steps (the state stays on chip between them), or a single step of at least 32 simulations.
+// One step of a few simulations is faster spread over all SMs by the phase kernels (tools/step_latency.py: 37 us
+// against 45 us per step() at batch 1; the fused launch also reads and writes the state, ~10 us).
+static int pick_step_kernel(const smk_grid_t* g, const smk_params_t* prm, int nsteps, int* fused)
 {
     *fused = 0;
     if (prm->step_kernel == SMK_STEP_PHASES) return SMK_OK;
     if (prm->step_kernel != SMK_STEP_AUTO && prm->step_kernel != SMK_STEP_FUSED)
         return fail(SMK_EINVAL, "smk_step: step_kernel %d is not SMK_STEP_AUTO/_PHASES/_FUSED", prm->step_kernel);
-    if (fused_supported(g)) { *fused = 1; return SMK_OK; }
+    if (fused_supported(g)) {
+        *fused = (prm->step_kernel == SMK_STEP_FUSED || nsteps >= 2 || g->batch >= 32) ? 1 : 0;
+        return SMK_OK;
+    }
     if (prm->step_kernel == SMK_STEP_FUSED)
         return fail(SMK_EUNSUPPORTED, "smk_step: SMK_STEP_FUSED needs a non-slab grid of at most 128 x 128 cells, got %d x %d", g->h, g->w);
     return SMK_OK;
 }
 
-int smk_step_is_fused(const smk_grid_t* g, const smk_params_t* prm, int32_t* fused_host)
+int smk_step_is_fused(const smk_grid_t* g, const smk_params_t* prm, int32_t nsteps, int32_t* fused_host)
 {
     SMK_TRY(check_grid(g, "smk_step_is_fused"));
     if (!prm || !fused_host) return fail(SMK_EINVAL, "smk_step_is_fused: NULL");
     int f = 0;
-    SMK_TRY(pick_step_kernel(g, prm, &f));
+    SMK_TRY(pick_step_kernel(g, prm, nsteps, &f));
     *fused_host = f;
     return SMK_OK;
 }
@@ -282,7 +289,7 @@ int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, floa
     if (!(prm->dt != 0.0f)) return fail(SMK_EINVAL, "smk_step: dt must be non-zero");
     cudaStream_t s = (cudaStream_t)stream;
     int fused = 0;
-    SMK_TRY(pick_step_kernel(g, prm, &fused));
+    SMK_TRY(pick_step_kernel(g, prm, 1, &fused));
     if (fused)
         return launch_steps_fused(g, st->u[st->cur_u], st->v[st->cur_v], st->d[st->cur_d], st->p[st->cur_p], 1, frame, 0, frame_stride,
                                   fmul, prm->dt, prm->c_uv, prm->c_d, prm->decay, prm->jacobi_iters, s);
@@ -310,7 +317,7 @@ int smk_run_steps(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
         // the fused kernel keeps the state on chip across all the steps of the call: one launch
         SMK_TRY(check_grid(g, "smk_run_steps"));
         int fused = 0;
-        SMK_TRY(pick_step_kernel(g, prm, &fused));
+        SMK_TRY(pick_step_kernel(g, prm, nsteps, &fused));
         if (fused) {
             SMK_TRY(check_ptrs("smk_run_steps", {st->u[0], st->u[1], st->v[0], st->v[1], st->d[0], st->d[1], st->p[0], st->p[1]}));
             if ((st->cur_u | st->cur_v | st->cur_d | st->cur_p) & ~1) return fail(SMK_EINVAL, "smk_run_steps: cur_* must be 0 or 1");

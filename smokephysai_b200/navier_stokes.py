@@ -8,7 +8,8 @@ bilinear_interpolate, pressure_projection, step) as the reference class, so call
 `jacobi_iters=20` (the literal at navier_stokes.py:139), `batch=1` (independent simulations; fields gain
 a leading dimension when batch > 1), `sweeps_per_launch=0` (temporal-blocking depth, 0 = library default),
 `step_kernel="auto"` ("fused": whole simulation on one SM, all steps of a call in one launch, grids up to
-128 x 128; "phases": one kernel per phase; "auto": fused when the grid qualifies -- bit-identical results).
+128 x 128; "phases": one kernel per phase; "auto": fused when the grid qualifies and the call is run_steps(n >= 2)
+or carries at least 32 simulations -- bit-identical results either way).
 
 There is no CPU compute path.  `device='cpu'` (benchmark.py:260 passes it) only means "hand results back
 as CPU tensors": the step always runs on the current CUDA device.
@@ -179,11 +180,11 @@ class NavierStokesSimulator(nn.Module):
         return Params(dt, dt * nu, dt * (nu * 0.1), 0.995, int(self.jacobi_iters), int(self.sweeps_per_launch),
                       _lib.STEP_KERNELS[self.step_kernel])
 
-    def step_is_fused(self):
-        """True when step() / run_steps() take the single-launch on-chip path for this grid."""
+    def step_is_fused(self, nsteps=1):
+        """True when a call of nsteps steps (step(): 1, run_steps(n): n) takes the single-launch on-chip path."""
         flag = C.c_int32(0)
         prm = self._params()
-        _lib.call("smk_step_is_fused", C.byref(self._grid), C.byref(prm), C.byref(flag))
+        _lib.call("smk_step_is_fused", C.byref(self._grid), C.byref(prm), int(nsteps), C.byref(flag))
         return bool(flag.value)
 
     def _to_out(self, t):
@@ -236,8 +237,20 @@ class NavierStokesSimulator(nn.Module):
         src_h = torch.from_numpy(rec.view(np.uint8))
         off_h = torch.tensor(offs, dtype=torch.int32)
         if pin:
-            src_h, off_h = src_h.pin_memory(), off_h.pin_memory()
-        return src_h.to(self._cuda, non_blocking=pin), off_h.to(self._cuda, non_blocking=pin), src_h.numel() + 4 * off_h.numel()
+            # one cached pinned staging buffer (cudaHostAlloc per call costs more than the copy); the previous
+            # call's H2D copy has long been consumed by the splat that followed it on the same stream
+            need = src_h.numel() + 4 * off_h.numel()
+            stage = getattr(self, "_pinned_sources", None)
+            if stage is None or stage.numel() < need:
+                stage = torch.empty(max(need, 4096), dtype=torch.uint8).pin_memory()
+                self._pinned_sources = stage
+            else:
+                torch.cuda.current_stream(self._cuda).synchronize()
+            stage[:src_h.numel()].copy_(src_h)
+            stage[src_h.numel():need].view(torch.int32).copy_(off_h)
+            dev = stage[:need].to(self._cuda, non_blocking=True)
+            return dev[:src_h.numel()], dev[src_h.numel():need].view(torch.int32), need
+        return src_h.to(self._cuda), off_h.to(self._cuda), src_h.numel() + 4 * off_h.numel()
 
     def splat_uploaded(self, src, off):
         _lib.call("smk_splat_sources", C.byref(self._grid), self._ptr("d"), src.data_ptr(), off.data_ptr(), self._stream())

@@ -78,7 +78,7 @@ class SmokeSimulator(nn.Module):
         dev, host, cs = self._gen_dev, self._gen_host, self._gen_copy_stream
         main = torch.cuda.current_stream(ns._cuda)
         cs.wait_stream(main)                      # the previous call's consumer is done with the buffers
-        n = int(steps_per_copy) if steps_per_copy else (2 if ns.step_is_fused() else 1)
+        n = int(steps_per_copy) if steps_per_copy else (2 if ns.step_is_fused(2) else 1)
         for t in range(0, T, n):
             m = min(n, T - t)
             ns.run_steps_time_major(m, dev[t:t + m], fmul=fmul)

@@ -40,17 +40,23 @@ def random_state(h, w, seed, vel=300.0):
 
 
 def test_dispatch_rules():
-    assert make(128, 128).step_is_fused()
-    assert make(2, 2).step_is_fused()
-    assert make(96, 40, batch=3).step_is_fused()
-    assert not make(128, 128, step_kernel="phases").step_is_fused()
-    assert not make(129, 128).step_is_fused()
-    assert not make(128, 132).step_is_fused()
-    assert not make(1, 64).step_is_fused()
+    """auto: the one-simulation-per-SM kernel needs enough work per launch -- several steps, or >= 32 simulations."""
+    assert not make(128, 128).step_is_fused()               # one step of one simulation: phase kernels over all SMs
+    assert make(128, 128).step_is_fused(nsteps=2)
+    assert make(128, 128, batch=32).step_is_fused()
+    assert not make(96, 40, batch=3).step_is_fused() and make(96, 40, batch=3).step_is_fused(20)
+    assert make(128, 128, step_kernel="fused").step_is_fused() and make(2, 2, step_kernel="fused").step_is_fused()
+    assert not make(128, 128, batch=64, step_kernel="phases").step_is_fused(20)
+    for big in ((129, 128), (128, 132), (1, 64)):
+        assert not make(*big, batch=64).step_is_fused(20)
     with pytest.raises(_lib.SmokeLibraryError, match="128 x 128"):
         make(256, 256, step_kernel="fused").step()
     with pytest.raises(ValueError):
         make(64, 64, step_kernel="tensor-cores")
+    # the dispatch is observable in the launch count: 6 phase kernels against 1 fused launch
+    ns = make(128, 128)
+    n0 = _lib.launch_count(); ns.step(); n1 = _lib.launch_count(); ns.run_steps(3); n2 = _lib.launch_count()
+    assert (n1 - n0, n2 - n1) == (6, 1)
 
 
 @pytest.mark.parametrize("h,w,K", [
