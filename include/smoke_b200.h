@@ -100,7 +100,8 @@ typedef struct smk_params {
  *                    for all the steps of the call in a single launch; grids of at most 128 x 128 cells only
  *                    (SMK_EUNSUPPORTED otherwise)
  *   SMK_STEP_AUTO    fused when the grid qualifies and the call carries enough work for one-simulation-per-SM
- *                    execution to win: two or more steps per call, or one step of at least 32 simulations */
+ *                    execution to win: at least 96 x 96 cells, and two or more steps per call or one step of at
+ *                    least 32 simulations                                                                   */
 enum { SMK_STEP_AUTO = 0, SMK_STEP_PHASES = 1, SMK_STEP_FUSED = 2 };
 
 SMK_API int smk_version(void);

@@ -258,7 +258,10 @@ static int pick_step_kernel(const smk_grid_t* g, const smk_params_t* prm, int ns
     if (prm->step_kernel != SMK_STEP_AUTO && prm->step_kernel != SMK_STEP_FUSED)
         return fail(SMK_EINVAL, "smk_step: step_kernel %d is not SMK_STEP_AUTO/_PHASES/_FUSED", prm->step_kernel);
     if (fused_supported(g)) {
-        *fused = (prm->step_kernel == SMK_STEP_FUSED || nsteps >= 2 || g->batch >= 32) ? 1 : 0;
+        // a CTA costs the same whatever the grid size, so small grids are better off on the phase kernels:
+        // 96 x 96 still wins fused (63 against 77 us per step of 148 simulations), 64 x 64 loses (65 against 52)
+        const bool big_enough = (long)g->h * g->w >= 96L * 96L;
+        *fused = (prm->step_kernel == SMK_STEP_FUSED || (big_enough && (nsteps >= 2 || g->batch >= 32))) ? 1 : 0;
         return SMK_OK;
     }
     if (prm->step_kernel == SMK_STEP_FUSED)

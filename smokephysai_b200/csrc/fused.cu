@@ -67,28 +67,41 @@ __device__ __forceinline__ float zdiff_cell(const float* F, int pitch, int rows,
     return zdiff1(F[i * pitch + j], F[iu * pitch + j], F[id * pitch + j], F[i * pitch + jl], F[i * pitch + jr], c);
 }
 
-// Strip-mapped diffusion of the thread's 8 x 4 cells of a field whose rows [0, 128) x cols [0, 128) part is full
-// (ROWS, COLS in {128, 129}).  Rows slide through registers; the left / right neighbours of the strip come from
-// the adjacent lanes, replicate padding at the field's edge.
-template <int ROWS, int COLS, int PITCH>
-__device__ __forceinline__ void zdiffuse_strip_full(const float* F, const float c, float4 (&out)[FZ_R], const int r0, const int c0, const int lane)
+// Strip-mapped diffusion of the thread's 8 x 4 cells of a rows x cols field (rows <= 129, cols <= 129).  Rows slide
+// through registers (LDS.128); the left / right neighbours of the strip come from the adjacent lanes; replicate
+// padding (:57-66) is an index clamp on the rows and a select on the columns.  Cells outside the field get
+// finite garbage that the caller does not store.  In the FULL instantiation rows / cols are literals.
+template <int PITCH>
+__device__ __forceinline__ void zdiffuse_strip(const float* F, const int rows, const int cols, const float c, float4 (&out)[FZ_R],
+                                               const int r0, const int c0, const int lane)
 {
-    float4 up = zlds4(F + max(r0 - 1, 0) * PITCH + c0);
-    float4 cur = zlds4(F + r0 * PITCH + c0);
+    const int rlast = rows - 1, clast = cols - 1;
+    float4 up = zlds4(F + min(max(r0 - 1, 0), rlast) * PITCH + c0);
+    float4 cur = zlds4(F + min(r0, rlast) * PITCH + c0);
 #pragma unroll
     for (int r = 0; r < FZ_R; ++r) {
         const int i = r0 + r;
-        const float4 dn = zlds4(F + min(i + 1, ROWS - 1) * PITCH + c0);
+        const float4 dn = zlds4(F + min(i + 1, rlast) * PITCH + c0);
         float left = __shfl_up_sync(0xffffffffu, cur.w, 1);
         float right = __shfl_down_sync(0xffffffffu, cur.x, 1);
         if (lane == 0) left = cur.x;
-        if (lane == 31) right = (COLS > 128) ? F[i * PITCH + 128] : cur.w;
-        out[r].x = zdiff1(cur.x, up.x, dn.x, left, cur.y, c);
-        out[r].y = zdiff1(cur.y, up.y, dn.y, cur.x, cur.z, c);
-        out[r].z = zdiff1(cur.z, up.z, dn.z, cur.y, cur.w, c);
-        out[r].w = zdiff1(cur.w, up.w, dn.w, cur.z, right, c);
+        if (lane == 31 && clast >= 128) right = F[min(i, rlast) * PITCH + 128];       // the staggered column of v
+        out[r].x = zdiff1(cur.x, up.x, dn.x, left, (c0 + 1 <= clast) ? cur.y : cur.x, c);
+        out[r].y = zdiff1(cur.y, up.y, dn.y, cur.x, (c0 + 2 <= clast) ? cur.z : cur.y, c);
+        out[r].z = zdiff1(cur.z, up.z, dn.z, cur.y, (c0 + 3 <= clast) ? cur.w : cur.z, c);
+        out[r].w = zdiff1(cur.w, up.w, dn.w, cur.z, (c0 + 4 <= clast) ? right : cur.w, c);
         up = cur; cur = dn;
     }
+}
+
+// zero the components of a strip float4 that lie at or beyond column `cols` (the padding columns stay zero)
+__device__ __forceinline__ float4 zmask4(float4 v, const int c0, const int cols)
+{
+    if (c0 + 0 >= cols) v.x = 0.f;
+    if (c0 + 1 >= cols) v.y = 0.f;
+    if (c0 + 2 >= cols) v.z = 0.f;
+    if (c0 + 3 >= cols) v.w = 0.f;
+    return v;
 }
 
 // Four IEEE quotients n / d (navier_stokes.py:136 divides by dt).  nvcc's div.rn.f32 has a fast path (three FFMAs
@@ -308,54 +321,24 @@ k_step_fused(const FusedArgs a)
             float4 R[FZ_R];
             float X = 0.f;
             // u
-            if (FULL) zdiffuse_strip_full<129, 128, FZ_PU>(su, a.c_uv, R, r0, c0, lane);
-            else {
-#pragma unroll
-                for (int r = 0; r < FZ_R; ++r) {
-                    const int i = r0 + r;
-                    float o[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) o[k] = (i <= h && c0 + k < w) ? zdiff_cell(su, FZ_PU, h + 1, w, i, c0 + k, a.c_uv) : 0.f;
-                    R[r] = make_float4(o[0], o[1], o[2], o[3]);
-                }
-            }
+            zdiffuse_strip<FZ_PU>(su, h + 1, w, a.c_uv, R, r0, c0, lane);
             if (xu) X = zdiff_cell(su, FZ_PU, h + 1, w, 128, xe, a.c_uv);
             __syncthreads();
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r) { const int i = r0 + r; if (FULL || (i <= h && colin)) zsts4(su + i * FZ_PU + c0, R[r]); }
+            for (int r = 0; r < FZ_R; ++r) { const int i = r0 + r; if (FULL || (i <= h && colin)) zsts4(su + i * FZ_PU + c0, FULL ? R[r] : zmask4(R[r], c0, w)); }
             if (xu) su[128 * FZ_PU + xe] = X;
             // v (reads sv only: no barrier needed after the u write-back)
-            if (FULL) zdiffuse_strip_full<128, 129, FZ_PV>(sv, a.c_uv, R, r0, c0, lane);
-            else {
-#pragma unroll
-                for (int r = 0; r < FZ_R; ++r) {
-                    const int i = r0 + r;
-                    float o[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) o[k] = (i < h && c0 + k <= w) ? zdiff_cell(sv, FZ_PV, h, w + 1, i, c0 + k, a.c_uv) : 0.f;
-                    R[r] = make_float4(o[0], o[1], o[2], o[3]);
-                }
-            }
+            zdiffuse_strip<FZ_PV>(sv, h, w + 1, a.c_uv, R, r0, c0, lane);
             if (xv) X = zdiff_cell(sv, FZ_PV, h, w + 1, xe, 128, a.c_uv);
             __syncthreads();
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r) { const int i = r0 + r; if (FULL || (i < h && c0 <= w)) zsts4(sv + i * FZ_PV + c0, R[r]); }
+            for (int r = 0; r < FZ_R; ++r) { const int i = r0 + r; if (FULL || (i < h && c0 <= w)) zsts4(sv + i * FZ_PV + c0, FULL ? R[r] : zmask4(R[r], c0, w + 1)); }
             if (xv) sv[xe * FZ_PV + 128] = X;
             // density
-            if (FULL) zdiffuse_strip_full<128, 128, FZ_PD>(sd, a.c_d, R, r0, c0, lane);
-            else {
-#pragma unroll
-                for (int r = 0; r < FZ_R; ++r) {
-                    const int i = r0 + r;
-                    float o[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) o[k] = (i < h && c0 + k < w) ? zdiff_cell(sd, FZ_PD, h, w, i, c0 + k, a.c_d) : 0.f;
-                    R[r] = make_float4(o[0], o[1], o[2], o[3]);
-                }
-            }
+            zdiffuse_strip<FZ_PD>(sd, h, w, a.c_d, R, r0, c0, lane);
             __syncthreads();
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r) { const int i = r0 + r; if (FULL || (i < h && colin)) zsts4(sd + i * FZ_PD + c0, R[r]); }
+            for (int r = 0; r < FZ_R; ++r) { const int i = r0 + r; if (FULL || (i < h && colin)) zsts4(sd + i * FZ_PD + c0, FULL ? R[r] : zmask4(R[r], c0, w)); }
             __syncthreads();
         }
 

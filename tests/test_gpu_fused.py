@@ -44,7 +44,8 @@ def test_dispatch_rules():
     assert not make(128, 128).step_is_fused()               # one step of one simulation: phase kernels over all SMs
     assert make(128, 128).step_is_fused(nsteps=2)
     assert make(128, 128, batch=32).step_is_fused()
-    assert not make(96, 40, batch=3).step_is_fused() and make(96, 40, batch=3).step_is_fused(20)
+    assert not make(96, 40, batch=64).step_is_fused(20) and make(96, 96, batch=3).step_is_fused(20)     # small grids: phases
+    assert not make(100, 120, batch=3).step_is_fused()
     assert make(128, 128, step_kernel="fused").step_is_fused() and make(2, 2, step_kernel="fused").step_is_fused()
     assert not make(128, 128, batch=64, step_kernel="phases").step_is_fused(20)
     for big in ((129, 128), (128, 132), (1, 64)):
