@@ -109,6 +109,27 @@ def sweep_split(K, T):
     return out
 
 
+def needs_single_exchange(world, halo, K):
+    """Deep halo: the pressure ghosts stay exact through all K sweeps of a step, so one exchange per step suffices."""
+    return world > 1 and halo >= int(K) + 4
+
+
+def build_step_plan(world, K, T, single_exchange, fdd, jacobi, project_advect):
+    """The step as a list of ("x", field names) halo exchanges and ("c", callable) compute phases.  Shared by
+    SlabNavierStokes and the CPU mirror in tests/slab_oracle.py, so the exchange schedule itself is what the CPU
+    tests check against the undecomposed oracle."""
+    plan = []
+    if world > 1:
+        plan.append(("x", ("u", "v", "d", "p") if single_exchange else ("u", "v", "d")))
+    plan.append(("c", fdd))
+    for t in sweep_split(K, T):
+        plan.append(("c", (lambda t=t: jacobi(t))))
+        if world > 1 and not single_exchange:
+            plan.append(("x", ("p",)))
+    plan.append(("c", project_advect))
+    return plan
+
+
 class DistExchanger:
     """Halo exchange over torch.distributed point-to-point ops (NCCL send/recv on GPUs, gloo on CPU)."""
 
@@ -217,7 +238,7 @@ class SlabNavierStokes:
         if world > 1 and self.halo < self.T + 3:
             raise ValueError("halo of %d rows is too shallow for %d fused sweeps per launch (need >= T + 3)" % (self.halo, self.T))
         # deep halo: the pressure ghosts stay exact through all K sweeps, one exchange per step (u, v, density, p)
-        self.single_exchange = world > 1 and self.halo >= int(jacobi_iters) + 4
+        self.single_exchange = needs_single_exchange(world, self.halo, jacobi_iters)
         self.geom = SlabGeometry(H, W, world, rank, self.halo if world > 1 else 0)
         self.grid_size, self.dt, self.viscosity = (H, W), dt, viscosity
         self.jacobi_iters = int(jacobi_iters)
@@ -316,16 +337,7 @@ class SlabNavierStokes:
 
     def step_plan(self):
         """The step as a list of ("x", field names) halo exchanges and ("c", callable) compute phases."""
-        plan = []
-        if self.world > 1:
-            plan.append(("x", ("u", "v", "d", "p") if self.single_exchange else ("u", "v", "d")))
-        plan.append(("c", self._fdd))
-        for t in sweep_split(self.jacobi_iters, self.T):
-            plan.append(("c", (lambda t=t: self._jacobi(t))))
-            if self.world > 1 and not self.single_exchange:
-                plan.append(("x", ("p",)))
-        plan.append(("c", self._project_advect))
-        return plan
+        return build_step_plan(self.world, self.jacobi_iters, self.T, self.single_exchange, self._fdd, self._jacobi, self._project_advect)
 
     def exchange_list(self, names):
         return [(self.full(n), self._kind(n)) for n in names]

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 import oracle
-from smokephysai_b200.slab import SlabGeometry, sweep_split
+from smokephysai_b200.slab import SlabGeometry, build_step_plan, needs_single_exchange
 
 
 class OracleSlab:
@@ -50,13 +50,5 @@ class OracleSlab:
         f["d"] = oracle.advection_step_slab(f["d"], f["u"], f["v"], dt, g.A, g.H) * np.float32(0.995)
 
     def step_plan(self):
-        plan = []
-        if self.world > 1:
-            plan.append(("x", ("u", "v", "d")))
-        plan.append(("c", self.fdd))
-        for t in sweep_split(self.K, self.T):
-            plan.append(("c", (lambda t=t: self.jacobi(t))))
-            if self.world > 1:
-                plan.append(("x", ("p",)))
-        plan.append(("c", self.project_advect))
-        return plan
+        single = needs_single_exchange(self.world, self.halo, self.K)
+        return build_step_plan(self.world, self.K, self.T, single, self.fdd, self.jacobi, self.project_advect)

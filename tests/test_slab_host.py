@@ -66,13 +66,19 @@ def test_geometry_rejects_thin_slabs():
         SlabGeometry(64, 32, 8, 0, 8)
 
 
-@pytest.mark.parametrize("world,K,T,H,W", [(2, 20, 10, 96, 40), (3, 13, 4, 90, 33), (4, 9, 1, 64, 24)])
-def test_local_emulation_matches_undecomposed_oracle(world, K, T, H, W):
+@pytest.mark.parametrize("world,K,T,H,W,halo", [
+    (2, 20, 10, 96, 40, None), (3, 13, 4, 90, 33, None), (4, 9, 1, 64, 24, None),
+    # deep halos (>= K + 4): ONE exchange per step, u, v, density and p together
+    (2, 20, 10, 96, 40, 24), (3, 9, 4, 90, 33, 13), (2, 6, 6, 64, 24, 12),
+])
+def test_local_emulation_matches_undecomposed_oracle(world, K, T, H, W, halo):
     """All slabs in one process (in-process halo copies): owned rows == the whole-grid oracle, bit for bit."""
     dt, nu, steps = 0.02, 0.01, 3
     st0 = random_state(H, W, seed=world * 100 + K)
     want = reference_run(st0, dt, nu, K, steps)
-    slabs = [OracleSlab((H, W), dt, nu, r, world, K, T) for r in range(world)]
+    slabs = [OracleSlab((H, W), dt, nu, r, world, K, T, halo=halo) for r in range(world)]
+    n_exchanges = sum(1 for kind, _ in slabs[0].step_plan() if kind == "x")
+    assert n_exchanges == (1 if halo is not None else 1 + len(sweep_split(K, T)))
     for s in slabs:
         for k in ("u", "v", "p", "d"):
             s.scatter(k, st0[k])
