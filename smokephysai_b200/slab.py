@@ -116,8 +116,8 @@ def needs_single_exchange(world, halo, K):
 
 def build_step_plan(world, K, T, single_exchange, fdd, jacobi, project_advect):
     """The step as a list of ("x", field names) halo exchanges and ("c", callable) compute phases.  Shared by
-    SlabNavierStokes and the CPU mirror in tests/slab_oracle.py, so the exchange schedule itself is what the CPU
-    tests check against the undecomposed oracle."""
+    SlabNavierStokes and the CPU mirror the tests drive, so the exchange schedule itself is what the CPU tests
+    check against the undecomposed run."""
     plan = []
     if world > 1:
         plan.append(("x", ("u", "v", "d", "p") if single_exchange else ("u", "v", "d")))
