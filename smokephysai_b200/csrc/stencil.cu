@@ -29,10 +29,14 @@ __device__ __forceinline__ float diff1(float f, float up, float dn, float l, flo
     s = s + r;
     return f + c * (s - 4.0f * f);
 }
+// The strip's left / right neighbours come from the adjacent lanes (a scalar LDS at a 4-word lane stride is a 4-way
+// bank conflict); lanes 0 and 31 read the staged halo columns.  Must be called by all 32 lanes of the warp.
 __device__ __forceinline__ float4 diff4(const float* up_row, const float* cur_row, const float* dn_row, int c4, float c)
 {
     const float4 up = lds4(up_row + c4), cur = lds4(cur_row + c4), dn = lds4(dn_row + c4);
-    const float l = cur_row[c4 - 1], r = cur_row[c4 + 4];
+    float l = __shfl_up_sync(0xffffffffu, cur.w, 1), r = __shfl_down_sync(0xffffffffu, cur.x, 1);
+    if (c4 == 4) l = cur_row[3];
+    if (c4 == 4 + 4 * 31) r = cur_row[132];
     float4 o;
     o.x = diff1(cur.x, up.x, dn.x, l, cur.y, c);
     o.y = diff1(cur.y, up.y, dn.y, cur.x, cur.z, c);
@@ -146,7 +150,8 @@ k_forces_diffuse_div(const float* __restrict__ U, const float* __restrict__ V, c
         if (i >= h) break;
         const float4 ua = lds4(&su1[r][4 * lane]), ub = lds4(&su1[r + 1][4 * lane]);
         const float4 va = lds4(&sv1[r][4 * lane]);
-        const float vr = sv1[r][4 * lane + 4];
+        float vr = __shfl_down_sync(0xffffffffu, va.x, 1);                 // v[i][j+1] of the strip's last cell: next lane
+        if (lane == 31) vr = sv1[r][128];
         float4 o;
         o.x = (((ub.x - ua.x) + va.y) - va.x) / dt;
         o.y = (((ub.y - ua.y) + va.z) - va.y) / dt;
