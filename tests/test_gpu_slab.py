@@ -139,3 +139,32 @@ def test_nccl_slabs_match_undecomposed(tmp_path, exch):
     for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
         ref = N(getattr(whole, name))
         assert_same(got[k][:, :ref.shape[1]], ref, "%s over NCCL, world %d" % (k, world))
+
+
+def test_full_size_c4_slabs_equal_undecomposed():
+    """BASELINE config 4 at full size: one 8192 x 8192 grid, K = 20, one emitter per 64 x 64 block.  Eight row slabs
+    (in-process halo copies, both exchange schedules) must equal the undecomposed run bit for bit after 2 steps."""
+    n, K = 8192, 20
+    rng = np.random.default_rng(4)
+    src = [(int(bx * 64 + rng.integers(8, 56)), int(by * 64 + rng.integers(8, 56)), 8, float(rng.uniform(0.5, 2.0)))
+           for by in range(n // 64) for bx in range(n // 64)]
+    whole = NavierStokesSimulator((n, n), device="cuda", jacobi_iters=K)
+    whole.add_sources([src])
+    for _ in range(2):
+        whole.step()
+    want = {k: getattr(whole, name).clone() for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density"))}
+    assert float(want["u"].abs().max()) > 0 and float(want["p"].abs().max()) > 0
+    del whole
+    torch.cuda.empty_cache()
+    for halo in (None, K + 4):                        # per-launch p exchanges (halo T + 4) and the single-exchange plan
+        grp = LocalGroup((n, n), device="cuda", world=8, jacobi_iters=K, sweeps_per_launch=10, halo=halo)
+        for s in grp.slabs:
+            s.add_sources(src)
+        for _ in range(2):
+            grp.step()
+        grp.check()
+        for k in ("u", "v", "p", "d"):
+            got = grp.gather(k)
+            assert torch.equal(got[:, :want[k].shape[1]], want[k]), "%s differs (halo %r)" % (k, halo)
+        del grp
+        torch.cuda.empty_cache()
