@@ -26,7 +26,10 @@ namespace smk {
 constexpr int FZ_R = 8, FZ_NW = 16, FZ_THREADS = FZ_NW * 32;
 constexpr int FZ_PU = 128, FZ_PV = 132, FZ_PD = 128;                 // shared-memory row pitches
 constexpr int FZ_SU = 129 * FZ_PU, FZ_SV = 128 * FZ_PV, FZ_SD = 128 * FZ_PD;     // floats
-constexpr int FZ_PMASK = 6;       // row pairs 1 and 2 of a sweep use f32x2 arithmetic, 0 and 3 scalar (fastest mix measured)
+#ifndef SMK_FZ_PMASK
+#define SMK_FZ_PMASK 7
+#endif
+constexpr int FZ_PMASK = SMK_FZ_PMASK;   // bit rr: row pair rr of a sweep uses f32x2 arithmetic (7: pairs 0-2 packed, 3 scalar; 6, 7, 15 are within 1 %)
 constexpr size_t FZ_SMEM = (size_t)(FZ_SU + FZ_SV + FZ_SD) * 4 + sizeof(float4) * 2 * 2 * FZ_NW * 32;
 
 // Phase timing for tools/micro/fused_probe.cu only (never defined in the library build): thread 0 of CTA 0
