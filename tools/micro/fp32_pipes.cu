@@ -39,6 +39,10 @@ __global__ void __launch_bounds__(512) k(float* out, float seed, float b)
                 if (k & 1) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(x[k]) : "f"(b));
                 else asm volatile("fma.rn.f32 %0, %0, 0f3F800000, %1;" : "+f"(x[k]) : "f"(b));
             }
+            if (MODE == 10) asm volatile("cvt.rmi.f32.f32 %0, %0;" : "+f"(x[k]));                       // FRND.FLOOR
+            if (MODE == 11) { int t; asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(t) : "f"(x[k])); asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(x[k]) : "r"(t)); }   // F2I + I2F
+            if (MODE == 12) asm volatile("min.f32 %0, %0, %1;" : "+f"(x[k]) : "f"(b));                  // FMNMX
+            if (MODE == 13) { asm volatile("cvt.rmi.f32.f32 %0, %0;" : "+f"(x[k])); asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(x[(k + 3) % NACC]) : "f"(b)); }  // FRND + FADD
             if (MODE == 9) {       // add with two varying register operands (neighbour accumulators)
                 asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(x[k]) : "f"(x[(k + 5) % NACC]));
             }
@@ -92,6 +96,10 @@ int main()
         run<7>("mix: 1 FADD2 + 2 FADD per 4 results", NACC, w);
         run<8>("mix: FADD r,r + FFMA r,1.0,r", NACC, w);
         run<9>("FADD r,r' (two varying regs)", NACC, w);
+        run<10>("FRND.FLOOR", NACC, w);
+        run<11>("F2I + I2F (counted as 2 results)", 2 * NACC, w);
+        run<12>("FMNMX", NACC, w);
+        run<13>("FRND + FADD interleaved (2 results)", 2 * NACC, w);
     }
     return 0;
 }
