@@ -459,6 +459,12 @@ def main():
         "note": note,
     }
     step_bytes = 100 + 12 * K
+    # fp32 adds / multiplies / divides of one cell-step, counted from the reference's expressions (no FMA by the
+    # bit-parity contract, so one instruction = one flop): buoyancy 3, diffusion 3 x 7, divergence 4, Jacobi 5 K,
+    # gradient subtract 6, advection 3 x 27, decay 1, fractal multiply 2.  Clamps, floors and index math not counted.
+    step_flops = 118 + 5 * K
+    sm_count, sm_mhz = torch.cuda.get_device_properties(dev).multi_processor_count, (clk or {}).get("sm_mhz") or 1965.0
+    fp32_peak = sm_count * 128 * sm_mhz * 1e6 / 1e12            # 128 fp32 lanes per SM, one add or multiply per lane per clock
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
@@ -474,6 +480,10 @@ def main():
         "roofline": roofline,
         "roofline_step": {"algorithmic_bytes_per_cell_step": step_bytes, "achieved": value / world * step_bytes / 1e9, "peak": peak,
                           "unit": "GB/s", "frac": value / world * step_bytes / 1e9 / peak, "per": "GPU (owned cells only; ghost-row recompute not counted)"},
+        "roofline_fp32": {"bound": "fp32 issue (what actually bounds the on-chip kernels; the HBM roofline above is the contract's)",
+                          "flops_per_cell_step": step_flops, "achieved": value / world * step_flops / 1e12, "peak": fp32_peak,
+                          "unit": "Tflop/s per GPU, non-FMA fp32", "frac": value / world * step_flops / 1e12 / fp32_peak,
+                          "peak_source": "%d SMs x 128 lanes x %.0f MHz (tools/micro/fp32_pipes.cu measures 118 of 128 results/clk/SM)" % (sm_count, sm_mhz)},
         "phases_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
     }
     if not args.no_cpu_baseline:
