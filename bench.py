@@ -111,7 +111,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "--format=csv,noheader,nounits", "-lms", "25"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -245,7 +245,7 @@ def reference_torch_numbers(dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -397,7 +397,6 @@ def main():
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - n0 + (replayed[0] - r0) * replayed[1]      # kernels inside replayed graphs count too
-    clk = clocks.stop() if rank == 0 else None
     value = total_cells_per_step * args.steps / (ms * 1e-3)
 
     # ---- per-kernel shares (second pass over the same steps, events around every launch) ------------------
@@ -407,6 +406,9 @@ def main():
         device_step(eager=True)          # per-launch events cannot be recorded inside a replayed graph
     torch.cuda.synchronize()
     prof = _lib.profile_end()
+    # clocks / throttle reasons were sampled from before the timed region to here: the timed steps and the same
+    # steps once more for the per-kernel events, i.e. only while the GPU runs the measured kernels
+    clk = clocks.stop() if rank == 0 else None
 
     # ---- end to end through the public API: host emitter lists -> results in pinned host memory ------------
     for _ in range(2):
