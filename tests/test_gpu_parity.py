@@ -8,6 +8,7 @@ and sinf/cosf in the Perlin octaves (<= 5e-7 absolute).  north_star's 1e-4 is th
 four orders of margin; the tests assert the tighter bound.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -387,3 +388,29 @@ def test_abi_rejects_bad_arguments():
     assert lib.smk_divergence(C.byref(bad), st.u[0], st.v[0], st.div, 0.01, None) == -1
     with pytest.raises(_lib.SmokeLibraryError):
         _lib.call("smk_diffuse", st.u[0], st.u[0], 4, 4, 4, 1, 16, 0.1, None)
+
+
+@pytest.mark.parametrize("tile", [1, 2, 3])
+@pytest.mark.parametrize("h,w,K,T_", [(300, 200, 33, 8), (130, 520, 20, 10), (1030, 260, 24, 12)])
+def test_jacobi_every_tile_shape_vs_oracle(tile, h, w, K, T_):
+    """The tiled Jacobi picks its CTA tile by grid size (128 x 128 one CTA per SM, 64 x 128 two CTAs per SM for grids of
+    many CTA waves); every shape must give the oracle's pressure bit for bit.  SMK_JACOBI_TILE forces the shape."""
+    rng = np.random.default_rng(tile * 100 + h)
+    p = rng.standard_normal((h, w)).astype(np.float32)
+    div = rng.standard_normal((h, w)).astype(np.float32)
+    ns = make(h, w, K=K, sweeps_per_launch=T_)
+    ns.p = T(p)
+    ns._field("div").copy_(T(div))
+    st = ns._state
+    flag = C.c_int32(0)
+    old = os.environ.get("SMK_JACOBI_TILE")
+    os.environ["SMK_JACOBI_TILE"] = str(tile)
+    try:
+        _lib.call("smk_jacobi", C.byref(ns._grid), st.div, st.p[0], st.p[1], K, T_, C.byref(flag), ns._stream())
+    finally:
+        if old is None:
+            del os.environ["SMK_JACOBI_TILE"]
+        else:
+            os.environ["SMK_JACOBI_TILE"] = old
+    st.cur_p = flag.value
+    assert_same(N(ns.p), oracle.jacobi(p, div, K), "jacobi tile %d" % tile)
