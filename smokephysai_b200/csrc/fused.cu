@@ -151,10 +151,9 @@ __device__ __forceinline__ float zadvect_cell(const float* F, const int rows, co
     py = fminf(fmaxf(py, 0.0f), ymax);
     const float fx0 = floorf(px), fy0 = floorf(py);
     const float fx1 = fminf(fx0 + 1.0f, xmax), fy1 = fminf(fy0 + 1.0f, ymax);
-    const int x0 = (int)fx0, y0 = (int)fy0;
     const int dx = (fx1 != fx0) ? 1 : 0, dy = (fy1 != fy0) ? PITCH : 0;
     const float ax = fx1 - px, bx = px - fx0, ay = fy1 - py, by = py - fy0;
-    const float* q = F + (y0 * PITCH + x0);
+    const float* q = F + (int)__fmaf_rn(fy0, (float)PITCH, fx0);           // exact in fp32 (< 2^24), one conversion
     float s = (ax * ay) * q[0] + (bx * ay) * q[dx];
     s = s + (ax * by) * q[dy];
     s = s + (bx * by) * q[dy + dx];
@@ -198,8 +197,10 @@ __device__ __forceinline__ float2 zadvect_pair(const float* F, const int rows, c
     fy1.x = fminf(fy1.x, ymax); fy1.y = fminf(fy1.y, ymax);
     const float2 ax = __fadd2_rn(fx1, zneg2(px)), bx = __fadd2_rn(px, zneg2(fx0));
     const float2 ay = __fadd2_rn(fy1, zneg2(py)), by = __fadd2_rn(py, zneg2(fy0));
-    const float* q0 = F + ((int)fy0.x * PITCH + (int)fx0.x);
-    const float* q1 = F + ((int)fy0.y * PITCH + (int)fx0.y);
+    // flat index y0 * PITCH + x0 formed in fp32 (integers below 2^24: exact) and converted once: the conversion pipe
+    // delivers 16 results per clock per SM, an eighth of the FP32 rate (tools/micro/fp32_pipes.cu)
+    const float* q0 = F + (int)__fmaf_rn(fy0.x, (float)PITCH, fx0.x);
+    const float* q1 = F + (int)__fmaf_rn(fy0.y, (float)PITCH, fx0.y);
     const int dx0 = (fx1.x != fx0.x) ? 1 : 0, dy0 = (fy1.x != fy0.x) ? PITCH : 0;
     const int dx1 = (fx1.y != fx0.y) ? 1 : 0, dy1 = (fy1.y != fy0.y) ? PITCH : 0;
     const float2 f00 = make_float2(q0[0], q1[0]), f01 = make_float2(q0[dx0], q1[dx1]);
