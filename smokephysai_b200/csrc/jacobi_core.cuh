@@ -128,18 +128,23 @@ __device__ __forceinline__ void packed_zero_rows(PackedStrip& S, const unsigned 
 }
 
 // One sweep S -> Dst, boundary rows (0 and 7) first: they are posted to shared memory for the neighbouring
-// warps before the interior row pairs are computed.
+// warps before the interior row pairs are computed.  (INTERIOR_FIRST, probe builds: the other order, which hides
+// the latency of the halo loads instead of that of the posts.)
 __device__ __forceinline__ void mbar_arrive_cta(unsigned long long* b)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
 }
 
 // posted (optional, MBAR builds): an mbarrier every lane arrives on once its two boundary rows are in shared memory
-template <int PMASK, int DBG = 0, bool MBAR = false>
+template <int PMASK, int DBG = 0, bool MBAR = false, bool INTERIOR_FIRST = false>
 __device__ __forceinline__ void sweep_packed(const PackedStrip& S, PackedStrip& Dst, const PackedStrip& ND,
                                              const float4 uph, const float4 dnh, const float2 (&M)[4], const unsigned ringmask,
                                              float4* post_first, float4* post_last, unsigned long long* posted = nullptr)
 {
+    if (INTERIOR_FIRST) {
+        packed_pair<1, (PMASK & 2) != 0, DBG>(S, Dst, ND, uph, dnh, M);
+        packed_pair<2, (PMASK & 4) != 0, DBG>(S, Dst, ND, uph, dnh, M);
+    }
     packed_pair<0, (PMASK & 1) != 0, DBG>(S, Dst, ND, uph, dnh, M);
     packed_pair<3, (PMASK & 8) != 0, DBG>(S, Dst, ND, uph, dnh, M);
     if (ringmask & 0x81u) {
@@ -148,8 +153,10 @@ __device__ __forceinline__ void sweep_packed(const PackedStrip& S, PackedStrip& 
     }
     if (post_first) { *post_first = packed_row(Dst, 0); *post_last = packed_row(Dst, 7); }
     if (MBAR) mbar_arrive_cta(posted);
-    packed_pair<1, (PMASK & 2) != 0, DBG>(S, Dst, ND, uph, dnh, M);
-    packed_pair<2, (PMASK & 4) != 0, DBG>(S, Dst, ND, uph, dnh, M);
+    if (!INTERIOR_FIRST) {
+        packed_pair<1, (PMASK & 2) != 0, DBG>(S, Dst, ND, uph, dnh, M);
+        packed_pair<2, (PMASK & 4) != 0, DBG>(S, Dst, ND, uph, dnh, M);
+    }
     if (ringmask & 0x7eu) packed_zero_rows(Dst, ringmask & 0x7eu);
 }
 
