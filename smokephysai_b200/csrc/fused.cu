@@ -33,7 +33,7 @@ constexpr int FZ_PMASK = SMK_FZ_PMASK;   // bit rr: row pair rr of a sweep uses 
 #ifndef SMK_FZ_INTERIOR_FIRST
 #define SMK_FZ_INTERIOR_FIRST 1
 #endif
-constexpr bool FZ_INTERIOR_FIRST = SMK_FZ_INTERIOR_FIRST != 0;   // a sweep computes rows 1..6 before rows 0 and 7 (hides the halo loads): mask 6 + this order is 2.3 % faster on c2 than mask 7 + boundary rows first
+constexpr int FZ_ORDER = SMK_FZ_INTERIOR_FIRST;   // a sweep computes rows 1..6 before rows 0 and 7 (hides the halo loads): mask 6 + this order is 2.3 % faster on c2 than mask 7 + boundary rows first
 constexpr size_t FZ_SMEM = (size_t)(FZ_SU + FZ_SV + FZ_SD) * 4 + sizeof(float4) * 2 * 2 * FZ_NW * 32;
 
 // Phase timing for tools/micro/fused_probe.cu only (never defined in the library build): thread 0 of CTA 0
@@ -392,20 +392,20 @@ k_step_fused(const FusedArgs a)
                 {
                     const float4 up = warp > 0 ? halo[0][1][warp - 1][lane] : zero4;
                     const float4 dn = warp < FZ_NW - 1 ? halo[0][0][warp + 1][lane] : zero4;
-                    sweep_packed<FZ_PMASK, 0, false, FZ_INTERIOR_FIRST>(P, Q, ND, up, dn, M, ringmask, &halo[1][0][warp][lane], &halo[1][1][warp][lane]);
+                    sweep_packed<FZ_PMASK, 0, false, FZ_ORDER>(P, Q, ND, up, dn, M, ringmask, &halo[1][0][warp][lane], &halo[1][1][warp][lane]);
                     __syncthreads();
                 }
                 {
                     const float4 up = warp > 0 ? halo[1][1][warp - 1][lane] : zero4;
                     const float4 dn = warp < FZ_NW - 1 ? halo[1][0][warp + 1][lane] : zero4;
-                    sweep_packed<FZ_PMASK, 0, false, FZ_INTERIOR_FIRST>(Q, P, ND, up, dn, M, ringmask, &halo[0][0][warp][lane], &halo[0][1][warp][lane]);
+                    sweep_packed<FZ_PMASK, 0, false, FZ_ORDER>(Q, P, ND, up, dn, M, ringmask, &halo[0][0][warp][lane], &halo[0][1][warp][lane]);
                     __syncthreads();
                 }
             }
             if (s < a.K) {                  // odd K: one more sweep, the result moves back into P
                 const float4 up = warp > 0 ? halo[0][1][warp - 1][lane] : zero4;
                 const float4 dn = warp < FZ_NW - 1 ? halo[0][0][warp + 1][lane] : zero4;
-                sweep_packed<FZ_PMASK, 0, false, FZ_INTERIOR_FIRST>(P, Q, ND, up, dn, M, ringmask, &halo[1][0][warp][lane], &halo[1][1][warp][lane]);
+                sweep_packed<FZ_PMASK, 0, false, FZ_ORDER>(P, Q, ND, up, dn, M, ringmask, &halo[1][0][warp][lane], &halo[1][1][warp][lane]);
                 P = Q;
                 __syncthreads();
             }

@@ -136,21 +136,21 @@ k_jacobi_packed(const float* __restrict__ pin, float* __restrict__ pout, const f
         {
             const float4 up = warp > 0 ? halo[0][1][warp - 1][lane] : zero4;
             const float4 dn = warp < NW - 1 ? halo[0][0][warp + 1][lane] : zero4;
-            sweep_packed<PMASK, 0, false, true>(A, B, ND, up, dn, M, ringmask, &halo[1][0][warp][lane], &halo[1][1][warp][lane]);
+            sweep_packed<PMASK, 0, false, 1>(A, B, ND, up, dn, M, ringmask, &halo[1][0][warp][lane], &halo[1][1][warp][lane]);
             __syncthreads();
         }
         {
             const float4 up = warp > 0 ? halo[1][1][warp - 1][lane] : zero4;
             const float4 dn = warp < NW - 1 ? halo[1][0][warp + 1][lane] : zero4;
             const bool more = s + 2 < T;
-            sweep_packed<PMASK, 0, false, true>(B, A, ND, up, dn, M, ringmask, more ? &halo[0][0][warp][lane] : nullptr, more ? &halo[0][1][warp][lane] : nullptr);
+            sweep_packed<PMASK, 0, false, 1>(B, A, ND, up, dn, M, ringmask, more ? &halo[0][0][warp][lane] : nullptr, more ? &halo[0][1][warp][lane] : nullptr);
             if (more) __syncthreads();
         }
     }
     if (s < T) {                           // odd T: one more sweep, then move the result back into A
         const float4 up = warp > 0 ? halo[0][1][warp - 1][lane] : zero4;
         const float4 dn = warp < NW - 1 ? halo[0][0][warp + 1][lane] : zero4;
-        sweep_packed<PMASK, 0, false, true>(A, B, ND, up, dn, M, ringmask, nullptr, nullptr);
+        sweep_packed<PMASK, 0, false, 1>(A, B, ND, up, dn, M, ringmask, nullptr, nullptr);
         A = B;
     }
 

@@ -128,23 +128,22 @@ __device__ __forceinline__ void packed_zero_rows(PackedStrip& S, const unsigned 
 }
 
 // One sweep S -> Dst, boundary rows (0 and 7) first: they are posted to shared memory for the neighbouring
-// warps before the interior row pairs are computed.  (INTERIOR_FIRST, probe builds: the other order, which hides
-// the latency of the halo loads instead of that of the posts.)
+// warps before the interior row pairs are computed (ORDER 0), or one of the other orders below.
 __device__ __forceinline__ void mbar_arrive_cta(unsigned long long* b)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
 }
 
 // posted (optional, MBAR builds): an mbarrier every lane arrives on once its two boundary rows are in shared memory
-template <int PMASK, int DBG = 0, bool MBAR = false, bool INTERIOR_FIRST = false>
+template <int PMASK, int DBG = 0, bool MBAR = false, int ORDER = 0>
 __device__ __forceinline__ void sweep_packed(const PackedStrip& S, PackedStrip& Dst, const PackedStrip& ND,
                                              const float4 uph, const float4 dnh, const float2 (&M)[4], const unsigned ringmask,
                                              float4* post_first, float4* post_last, unsigned long long* posted = nullptr)
 {
-    if (INTERIOR_FIRST) {
-        packed_pair<1, (PMASK & 2) != 0, DBG>(S, Dst, ND, uph, dnh, M);
-        packed_pair<2, (PMASK & 4) != 0, DBG>(S, Dst, ND, uph, dnh, M);
-    }
+    // ORDER 0: boundary pairs, post, interior pairs;  1: interior pairs, boundary pairs, post;  2: pair 1, boundary pairs,
+    // post, pair 2 (the halo loads complete under pair 1, the posts under pair 2)
+    if (ORDER == 1 || ORDER == 2) packed_pair<1, (PMASK & 2) != 0, DBG>(S, Dst, ND, uph, dnh, M);
+    if (ORDER == 1) packed_pair<2, (PMASK & 4) != 0, DBG>(S, Dst, ND, uph, dnh, M);
     packed_pair<0, (PMASK & 1) != 0, DBG>(S, Dst, ND, uph, dnh, M);
     packed_pair<3, (PMASK & 8) != 0, DBG>(S, Dst, ND, uph, dnh, M);
     if (ringmask & 0x81u) {
@@ -153,10 +152,8 @@ __device__ __forceinline__ void sweep_packed(const PackedStrip& S, PackedStrip& 
     }
     if (post_first) { *post_first = packed_row(Dst, 0); *post_last = packed_row(Dst, 7); }
     if (MBAR) mbar_arrive_cta(posted);
-    if (!INTERIOR_FIRST) {
-        packed_pair<1, (PMASK & 2) != 0, DBG>(S, Dst, ND, uph, dnh, M);
-        packed_pair<2, (PMASK & 4) != 0, DBG>(S, Dst, ND, uph, dnh, M);
-    }
+    if (ORDER == 0) packed_pair<1, (PMASK & 2) != 0, DBG>(S, Dst, ND, uph, dnh, M);
+    if (ORDER == 0 || ORDER == 2) packed_pair<2, (PMASK & 4) != 0, DBG>(S, Dst, ND, uph, dnh, M);
     if (ringmask & 0x7eu) packed_zero_rows(Dst, ringmask & 0x7eu);
 }
 

@@ -9,7 +9,7 @@ namespace smk { int fail(int c, const char*, ...) { return c; } int check_launch
 using namespace smk;
 
 // DBG bit 0: no shuffles, bit 1: no CTA barrier, bit 2: no halo LDS/STS, bit 3: no FP (only exchange)
-template <int PMASK, int DBG, int NW, bool IFIRST = false>
+template <int PMASK, int DBG, int NW, int IFIRST = 0>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_probe(const float* __restrict__ pin, float* __restrict__ pout, const float* __restrict__ div, const int T)
 {
@@ -134,7 +134,7 @@ void run_desync(const char* name, float* p, float* q, float* d, int nb)
     printf("%-64s %7.4f us/sweep  (%5.0f cycles at 1965 MHz)  %s\n", name, us_per_sweep, us_per_sweep * 1965, cudaGetErrorString(cudaGetLastError()));
 }
 
-template <int PMASK, int DBG, bool IFIRST = false>
+template <int PMASK, int DBG, int IFIRST = 0>
 void run(const char* name, float* p, float* q, float* d, int nb)
 {
     cudaEvent_t e0, e1;
@@ -165,11 +165,13 @@ int main()
     run_desync<16>("scalar, neighbour mbarriers instead of the CTA barrier", p, q, d, sms);
     run_desync<6>("half packed, neighbour mbarriers", p, q, d, sms);
     run_desync<15>("packed, neighbour mbarriers", p, q, d, sms);
-    run<16, 0, true>("scalar, interior rows first", p, q, d, sms);
-    run<6, 0, true>("half packed, interior rows first", p, q, d, sms);
-    run<7, 0, true>("mask 7, interior rows first", p, q, d, sms);
-    run<15, 0, true>("packed, interior rows first", p, q, d, sms);
-    run<7, 0>("mask 7, complete", p, q, d, sms);
+    run<16, 0, 1>("scalar, interior rows first", p, q, d, sms);
+    run<6, 0, 1>("half packed, interior rows first", p, q, d, sms);
+    run<7, 0, 1>("mask 7, interior rows first", p, q, d, sms);
+    run<15, 0, 1>("packed, interior rows first", p, q, d, sms);
+    run<6, 0, 2>("half packed, order pair1 / boundary+post / pair2", p, q, d, sms);
+    run<15, 0, 2>("packed, order pair1 / boundary+post / pair2", p, q, d, sms);
+    run<16, 0, 2>("scalar, order pair1 / boundary+post / pair2", p, q, d, sms);
     run<16, 0>("scalar ping-pong, complete", p, q, d, sms);
     run<15, 0>("packed, complete", p, q, d, sms);
     run<6, 0>("half packed, complete", p, q, d, sms);
