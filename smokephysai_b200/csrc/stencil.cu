@@ -2,6 +2,7 @@
 // emitter splat, the divergence norms and the fractal multiplier field.  All kernels are HBM/L2-bound
 // stencils or gathers: coalesced row-major access, shared-memory staging with halos where a phase reuses
 // neighbours, no tensor cores (nothing here is a contraction).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace smk {
@@ -407,6 +408,222 @@ k_advect(const AdvectArgs a)
     }
 }
 
+// ---- the same on a shared-memory tile ---------------------------------------------------------------------------
+// k_advect above is bound by instruction issue and L1 wavefronts, not by DRAM (77 % issue slots, 76 % L1 data pipe,
+// 41 % DRAM at 8192^2; the same rate when the fields fit in L2): ~100 instructions per cell, a third of them 64-bit
+// address arithmetic and edge predicates, and a 4-cells-per-thread layout that spreads each scalar gather of a warp
+// over 512 B.  Here a CTA stages, with 16-byte cp.async copies, the 16 x 128 cell tile it produces -- the velocity
+// rows it samples and the advected field with a 4-cell halo -- and then works like the fused kernel's advection:
+// cyclic cell mapping (lane l owns cells l, l+32, l+64, l+96 of a row: every shared-memory gather of a warp hits 32
+// consecutive banks for sub-cell displacements), 32-bit shared-memory offsets, two cells at a time as f32x2 pairs
+// (every add that consumes a product stays scalar: ptxas contracts packed mul + add even under --fmad=false).
+// The code is instantiated twice: INTERIOR tiles (every cell, its velocity samples and the whole staged window lie
+// strictly inside the field: no edge predicate anywhere) and the general case.  A back-trace that leaves the staged
+// window (more than about three cells) falls back to global loads for that cell pair; results are identical.
+constexpr int AT_R = 16, AT_C = 128, AT_HB = 4;
+constexpr int AT_FP = AT_C + 2 * AT_HB, AT_FR = AT_R + 2 * AT_HB;      // staged field window: 24 rows x 136 columns
+constexpr int AT_UP = AT_C + 4, AT_VP = AT_C;                          // u tile 16 x 129 (pitch 132), v tile 17 x 128
+
+struct AdvectTile {
+    float sF[AT_FR][AT_FP];
+    float sU[AT_R][AT_UP];
+    float sV[AT_R + 1][AT_VP];
+};
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ float2 neg2(const float2 a) { return make_float2(-a.x, -a.y); }
+
+template <bool SLAB, bool INTERIOR>
+__device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, const float* F, const float* U, const float* V, float* O,
+                                            const size_t b, const int i0, const int j0)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int w = a.w, rows = a.rows, cols = a.cols, pitch = a.pitch;
+
+    // ---- stage: field window rows [i0-4, i0+20) x columns [j0-4, j0+132), u rows [i0, i0+16), v rows [i0, i0+17) ----
+    const int wy0 = INTERIOR ? i0 - AT_HB : max(i0 - AT_HB, 0), wy1 = INTERIOR ? i0 + AT_R + AT_HB : min(i0 + AT_R + AT_HB, rows);
+    const int wx0 = INTERIOR ? j0 - AT_HB : max(j0 - AT_HB, 0), wx1 = INTERIOR ? j0 + AT_C + AT_HB : min(j0 + AT_C + AT_HB, pitch);
+#pragma unroll
+    for (int rr = 0; rr < AT_FR / 8; ++rr) {                         // warp wp copies window rows wp, wp+8, wp+16
+        const int r = wp + 8 * rr, y = i0 - AT_HB + r;
+        if (INTERIOR || (y >= wy0 && y < wy1)) {
+            const int x = j0 - AT_HB + 4 * lane;
+            const int off = y * pitch + x;                             // signed: only dereferenced where it is in range
+            if (INTERIOR || (x >= wx0 && x < wx1)) cp_async16(&T.sF[r][4 * lane], F + off);
+            if (lane < 2 && (INTERIOR || (x + 128 >= wx0 && x + 128 < wx1))) cp_async16(&T.sF[r][128 + 4 * lane], F + (off + 128));
+        }
+    }
+    const int urows = a.h + 1;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int r = wp + 8 * rr, y = i0 + r;
+        if (INTERIOR || y < urows) {
+            const float* src = U + ((unsigned)y * a.pu + j0);
+            if (INTERIOR || j0 + 4 * lane < a.pu) cp_async16(&T.sU[r][4 * lane], src + 4 * lane);
+            if (lane == 0 && (INTERIOR || j0 + 128 < a.pu)) cp_async16(&T.sU[r][128], src + 128);
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) {
+        const int r = wp + 8 * rr, y = i0 + r;
+        if (r <= AT_R && (INTERIOR || y < a.h)) {
+            if (INTERIOR || j0 + 4 * lane < a.pv) cp_async16(&T.sV[r][4 * lane], V + ((unsigned)y * a.pv + j0 + 4 * lane));
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // slab: h is the GLOBAL cell-row count and gi the global row of this thread's cells; memory stays local
+    const int h = SLAB ? a.gh : a.h;
+    const int grows = SLAB ? rows - a.h + a.gh : rows;
+    const float2 half2 = make_float2(0.5f, 0.5f), dt2 = make_float2(a.dt, a.dt), one2 = make_float2(1.0f, 1.0f);
+    const float xmax = (float)(cols - 1), ymax = (float)(grows - 1);
+    const int jb = j0 + lane;
+    const float* sF0 = &T.sF[0][0];
+    const int wy_org = i0 - AT_HB, wx_org = j0 - AT_HB;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int ri = 2 * wp + rr, i = i0 + ri;                     // tile row, local field row (warp-uniform)
+        if (!INTERIOR && i >= rows) break;
+        const int gi = SLAB ? i + a.row0 : i;
+        const float fi = (float)gi;
+        const bool urow_ok = INTERIOR || gi <= h - 1;                              // u_i is 0 on u's last row     :97-102
+        const bool vrow_ok = INTERIOR || (gi <= h - 2 && (!SLAB || i + 1 < a.h));  // v_i is 0 on the last cell row :104-109
+        float val[4];
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            const int c = lane + 64 * kp, c1 = c + 32;                 // tile columns of the pair
+            const int j = jb + 64 * kp, j1 = j + 32;
+            // a9: u_i = 0.5*U[i][j] + 0.5*U[i][j+1] for j <= w-2;  v_i = 0.5*V[i][j] + 0.5*V[i+1][j] for j <= w-1; else 0
+            const bool cu0 = urow_ok && (INTERIOR || j <= w - 2), cu1 = urow_ok && (INTERIOR || j1 <= w - 2);
+            const bool cv0 = vrow_ok && (INTERIOR || j <= w - 1), cv1 = vrow_ok && (INTERIOR || j1 <= w - 1);
+            const float2 ua = make_float2(cu0 ? T.sU[ri][c] : 0.f, cu1 ? T.sU[ri][c1] : 0.f);
+            const float2 ub = make_float2(cu0 ? T.sU[ri][c + 1] : 0.f, cu1 ? T.sU[ri][c1 + 1] : 0.f);
+            const float2 va = make_float2(cv0 ? T.sV[ri][c] : 0.f, cv1 ? T.sV[ri][c1] : 0.f);
+            const float2 vb = make_float2(cv0 ? T.sV[ri + 1][c] : 0.f, cv1 ? T.sV[ri + 1][c1] : 0.f);
+            const float2 hua = __fmul2_rn(half2, ua), hub = __fmul2_rn(half2, ub);
+            const float2 hva = __fmul2_rn(half2, va), hvb = __fmul2_rn(half2, vb);
+            const float2 ui = make_float2(hua.x + hub.x, hua.y + hub.y);
+            const float2 vi = make_float2(hva.x + hvb.x, hva.y + hvb.y);
+            const float2 du = __fmul2_rn(dt2, ui), dv = __fmul2_rn(dt2, vi);
+            float2 px = make_float2((float)j - du.x, (float)j1 - du.y);                                     // :87
+            float2 py = make_float2(fi - dv.x, fi - dv.y);                                                  // :88
+            px.x = fminf(fmaxf(px.x, 0.0f), xmax); px.y = fminf(fmaxf(px.y, 0.0f), xmax);                   // :91
+            py.x = fminf(fmaxf(py.x, 0.0f), ymax); py.y = fminf(fmaxf(py.y, 0.0f), ymax);                   // :92
+            // a8 (:111-131) with x0 = floor(px) already inside [0, cols-1]
+            const float2 fx0 = make_float2(floorf(px.x), floorf(px.y)), fy0 = make_float2(floorf(py.x), floorf(py.y));
+            float2 fx1 = __fadd2_rn(fx0, one2), fy1 = __fadd2_rn(fy0, one2);
+            fx1.x = fminf(fx1.x, xmax); fx1.y = fminf(fx1.y, xmax);
+            fy1.x = fminf(fy1.x, ymax); fy1.y = fminf(fy1.y, ymax);
+            const float2 ax = __fadd2_rn(fx1, neg2(px)), bx = __fadd2_rn(px, neg2(fx0));
+            const float2 ay = __fadd2_rn(fy1, neg2(py)), by = __fadd2_rn(py, neg2(fy0));
+            const int x0a = (int)fx0.x, x0b = (int)fx0.y;
+            int y0a = (int)fy0.x, y0b = (int)fy0.y;
+            const int dxa = (fx1.x != fx0.x) ? 1 : 0, dxb = (fx1.y != fx0.y) ? 1 : 0;
+            int dya = (fy1.x != fy0.x) ? 1 : 0, dyb = (fy1.y != fy0.y) ? 1 : 0;
+            if (SLAB) {                                                         // global -> local row, kept inside the slab
+                y0a -= a.row0; y0b -= a.row0;
+                const int y1a = y0a + dya, y1b = y0b + dyb;
+                if (i >= a.need_lo && i < a.need_hi && a.overflow &&
+                    ((j < cols && (y0a < a.valid_lo || y1a >= a.valid_hi)) || (j1 < cols && (y0b < a.valid_lo || y1b >= a.valid_hi))))
+                    *a.overflow = 1;
+                if (y1a > rows - 1) dya = 0;
+                if (y1b > rows - 1) dyb = 0;
+                y0a = clampi(y0a, 0, rows - 1); y0b = clampi(y0b, 0, rows - 1);
+            }
+            // both cells of the pair inside the staged window (with room for the +1 corners)?
+            const int lya = y0a - wy_org, lxa = x0a - wx_org, lyb = y0b - wy_org, lxb = x0b - wx_org;
+            bool inwin;
+            if (INTERIOR) inwin = ((unsigned)lya < (unsigned)(AT_FR - 1)) & ((unsigned)lxa < (unsigned)(AT_FP - 1)) &
+                                  ((unsigned)lyb < (unsigned)(AT_FR - 1)) & ((unsigned)lxb < (unsigned)(AT_FP - 1));
+            else inwin = y0a >= wy0 && y0a + dya < wy1 && x0a >= wx0 && x0a + dxa < wx1 &&
+                         y0b >= wy0 && y0b + dyb < wy1 && x0b >= wx0 && x0b + dxb < wx1;
+            float2 f00, f01, f10, f11;
+            if (inwin) {
+                const float* qa = sF0 + (lya * AT_FP + lxa);
+                const float* qb = sF0 + (lyb * AT_FP + lxb);
+                const int oya = dya * AT_FP, oyb = dyb * AT_FP;
+                f00 = make_float2(qa[0], qb[0]); f01 = make_float2(qa[dxa], qb[dxb]);
+                f10 = make_float2(qa[oya], qb[oyb]); f11 = make_float2(qa[oya + dxa], qb[oyb + dxb]);
+            } else {
+                const float* qa = F + ((unsigned)y0a * pitch + x0a);
+                const float* qb = F + ((unsigned)y0b * pitch + x0b);
+                const int oya = dya * pitch, oyb = dyb * pitch;
+                f00 = make_float2(__ldg(qa), __ldg(qb)); f01 = make_float2(__ldg(qa + dxa), __ldg(qb + dxb));
+                f10 = make_float2(__ldg(qa + oya), __ldg(qb + oyb)); f11 = make_float2(__ldg(qa + oya + dxa), __ldg(qb + oyb + dxb));
+            }
+            const float2 t00 = __fmul2_rn(__fmul2_rn(ax, ay), f00), t01 = __fmul2_rn(__fmul2_rn(bx, ay), f01);
+            const float2 t10 = __fmul2_rn(__fmul2_rn(ax, by), f10), t11 = __fmul2_rn(__fmul2_rn(bx, by), f11);
+            float2 sum = make_float2(t00.x + t01.x, t00.y + t01.y);
+            sum.x = sum.x + t10.x; sum.y = sum.y + t10.y;
+            sum.x = sum.x + t11.x; sum.y = sum.y + t11.y;
+            if (a.has_scale) sum = __fmul2_rn(sum, make_float2(a.scale, a.scale));                          // :171
+            val[2 * kp] = sum.x; val[2 * kp + 1] = sum.y;
+        }
+        // coalesced scalar stores (a warp writes 128 B per instruction); the padding columns [cols, pitch) get zeros
+        float* orow = O + (unsigned)i * pitch;
+        if (INTERIOR) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) orow[jb + 32 * k] = val[k];
+            if (a.frame) {                                                          // :173 (+ fractal_generator.py:62)
+                float* frow = a.frame + b * a.frame_stride + (unsigned)i * a.frame_pitch;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float fr = val[k];
+                    if (a.fmul) fr = fr + __ldg(a.fmul + (unsigned)i * a.frame_pitch + jb + 32 * k) * fr;
+                    frow[jb + 32 * k] = fr;
+                }
+            }
+        } else {
+            float* frow = a.frame ? a.frame + b * a.frame_stride + (unsigned)i * a.frame_pitch : nullptr;
+            const float* mrow = a.fmul ? a.fmul + (unsigned)i * a.frame_pitch : nullptr;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = jb + 32 * k;
+                if (j < pitch) {
+                    const float x = (j < cols) ? val[k] : 0.0f;
+                    orow[j] = x;
+                    if (frow && j < a.frame_pitch) {
+                        float fr = x;
+                        if (mrow) fr = fr + __ldg(mrow + j) * fr;
+                        frow[j] = fr;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <bool SLAB>
+__global__ void __launch_bounds__(256)
+k_advect_tiled(const AdvectArgs a)
+{
+    __shared__ __align__(16) AdvectTile T;
+    const int i0 = blockIdx.y * AT_R, j0 = blockIdx.x * AT_C;
+    const size_t b = blockIdx.z;
+    const float* F = a.F + b * a.stride;
+    const float* U = a.U + b * a.su_;
+    const float* V = a.V + b * a.sv_;
+    float* O = a.O + b * a.stride;
+    asm volatile("" : "+l"(F));
+    asm volatile("" : "+l"(U));
+    asm volatile("" : "+l"(V));
+    asm volatile("" : "+l"(O));
+    // interior tile: the staged window and the tile's u / v rows lie inside the arrays, every cell is a field cell
+    // strictly before the last row / column of the (global) grid, so no sample is zeroed and nothing needs a bound
+    const int gi_last = (SLAB ? a.row0 : 0) + i0 + AT_R - 1;
+    const int h = SLAB ? a.gh : a.h;
+    const bool interior = i0 >= AT_HB && i0 + AT_R + AT_HB <= a.rows && j0 >= AT_HB && j0 + AT_C + AT_HB <= a.pitch &&
+                          j0 + AT_C + 4 <= a.pu && j0 + AT_C <= a.pv && i0 + AT_R + 1 <= a.h &&
+                          j0 + AT_C - 1 <= a.w - 2 && gi_last <= h - 2 && j0 + AT_C <= a.cols && j0 + AT_C <= a.frame_pitch;
+    if (interior) advect_tile<SLAB, true>(a, T, F, U, V, O, b, i0, j0);
+    else          advect_tile<SLAB, false>(a, T, F, U, V, O, b, i0, j0);
+}
+
 int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows, int cols, int pitch, int64_t stride,
                   const float* u, const float* v, float dt, float scale, float* frame, int64_t frame_stride,
                   const float* fmul, const smk_slab_check_t* chk, cudaStream_t s)
@@ -426,6 +643,14 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
     const unsigned long long nthreads = (unsigned long long)rows * a.ngroups;
     dim3 grid((unsigned)((nthreads + 255) / 256), g->batch);
     ProfScope prof_(rows == g->h + 1 ? SMK_PH_ADVECT_U : (cols == g->w + 1 ? SMK_PH_ADVECT_V : SMK_PH_ADVECT_D), s);
+    static int tiled = -1;
+    if (tiled < 0) { const char* e = getenv("SMK_ADVECT_TILED"); tiled = e ? atoi(e) : 1; }
+    if (tiled && (rows + AT_R - 1) / AT_R <= 65535) {
+        dim3 tgrid((unsigned)((pitch + AT_C - 1) / AT_C), (unsigned)((rows + AT_R - 1) / AT_R), g->batch);
+        if (slab) k_advect_tiled<true><<<tgrid, 256, 0, s>>>(a);
+        else      k_advect_tiled<false><<<tgrid, 256, 0, s>>>(a);
+        return check_launch("k_advect_tiled");
+    }
     if (slab) k_advect<true><<<grid, 256, 0, s>>>(a);
     else      k_advect<false><<<grid, 256, 0, s>>>(a);
     return check_launch("k_advect");
