@@ -478,3 +478,32 @@ def test_both_advection_kernels_in_slabs(force_advect_kernel, tiled):
     grp.check()
     for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
         assert_same(N(grp.gather(k))[:, :st0[k].shape[1]], N(getattr(whole, name)), "%s tiled %d" % (k, tiled))
+
+
+@pytest.mark.parametrize("bulk", [0, 1])
+@pytest.mark.parametrize("h,w", [(100, 400), (64, 300), (35, 260), (130, 1000), (48, 392)])
+def test_both_staging_paths_of_forces_diffuse_div_vs_oracle(bulk, h, w):
+    """k_forces_diffuse_div stages interior tiles with bulk cp.async copies on big grids (SMK_FDD_BULK forces it): both
+    paths, on grids that have interior AND edge tiles, against the oracle, bit for bit."""
+    old = os.environ.get("SMK_FDD_BULK")
+    os.environ["SMK_FDD_BULK"] = str(bulk)
+    try:
+        rng = np.random.default_rng(h + w + bulk)
+        ref = oracle.OracleSolver((h, w), 0.02, 0.01, 5)
+        ref.u = ((rng.random((h + 1, w)) - 0.5) * 40).astype(np.float32)
+        ref.v = ((rng.random((h, w + 1)) - 0.5) * 40).astype(np.float32)
+        ref.p = rng.standard_normal((h, w)).astype(np.float32)
+        ref.density = rng.random((h, w)).astype(np.float32)
+        ns = make(h, w, 0.02, 0.01, 5, step_kernel="phases")
+        for k in ("u", "v", "p", "density"):
+            setattr(ns, k, T(getattr(ref, k)))
+        for t in range(2):
+            ref.step()
+            ns.step()
+            for k in ("u", "v", "p", "density"):
+                assert_same(N(getattr(ns, k)), getattr(ref, k), "%dx%d bulk %d step %d %s" % (h, w, bulk, t, k))
+    finally:
+        if old is None:
+            del os.environ["SMK_FDD_BULK"]
+        else:
+            os.environ["SMK_FDD_BULK"] = old
