@@ -295,7 +295,7 @@ int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, floa
     SMK_TRY(pick_step_kernel(g, prm, 1, &fused));
     if (fused)
         return launch_steps_fused(g, st->u[st->cur_u], st->v[st->cur_v], st->d[st->cur_d], st->p[st->cur_p], 1, frame, 0, frame_stride,
-                                  fmul, prm->dt, prm->c_uv, prm->c_d, prm->decay, prm->jacobi_iters, s);
+                                  fmul, prm->dt, prm->c_uv, prm->c_d, prm->decay, prm->jacobi_iters, st->div, s);
     const int cu = st->cur_u, cv = st->cur_v, cd = st->cur_d;
     float *u0 = st->u[cu], *u1 = st->u[cu ^ 1], *v0 = st->v[cv], *v1 = st->v[cv ^ 1], *d0 = st->d[cd], *d1 = st->d[cd ^ 1];
     // 1-2. buoyancy + diffusion + divergence                                   navier_stokes.py:154-160, :136
@@ -328,7 +328,7 @@ int smk_run_steps(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
             if (!(prm->dt != 0.0f)) return fail(SMK_EINVAL, "smk_run_steps: dt must be non-zero");
             return launch_steps_fused(g, st->u[st->cur_u], st->v[st->cur_v], st->d[st->cur_d], st->p[st->cur_p], nsteps, frames,
                                       frame_step_stride, frame_batch_stride, fmul, prm->dt, prm->c_uv, prm->c_d, prm->decay,
-                                      prm->jacobi_iters, (cudaStream_t)stream);
+                                      prm->jacobi_iters, st->div, (cudaStream_t)stream);
         }
     }
     for (int t = 0; t < nsteps; ++t)

@@ -18,6 +18,8 @@
 //
 // Bit-exactness: the association above is kept literally; 0.25*x == x*0.25 in IEEE; no FMA (-fmad=false).
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>
 #include "common.cuh"
 #include "jacobi_core.cuh"
 
@@ -168,6 +170,213 @@ k_jacobi_packed(const float* __restrict__ pin, float* __restrict__ pout, const f
     }
 }
 
+// ---- streaming variant for grids of many tiles -------------------------------------------------------------------
+// One persistent CTA per SM walks over 128 x 128 tiles; while it sweeps the tile it holds in registers, the next
+// tile's pressure and divergence (128 KB) are already on their way into shared memory, so the tile load overlaps
+// the arithmetic without needing a second resident CTA (k_jacobi_packed gets that overlap from two 64 x 128 CTAs
+// per SM, at the price of keeping only 44 of 64 rows per launch of 10 sweeps; here 108 of 128 survive).
+// Two staging engines (template parameter TMA):
+//   TMA   -- two cp.async.bulk.tensor.3d loads per tile (pressure, divergence: a 128 x 128 x 1 box of a (pitch, h, batch)
+//            tensor map, out-of-domain elements zero-filled by the TMA unit), issued by one thread after the CTA barrier
+//            that follows the strip reads and completed on one mbarrier.  The staging costs the LSU / MIO pipe nothing
+//            while the sweeps run.  (One cp.async.bulk per tile ROW -- 256 UBLKCP per tile -- was tried first: the issuing
+//            lanes stall on every copy and the tile took 4.7 us of overhead against 3.1 us with LDGSTS.)
+//   !TMA  -- 16-byte cp.async (LDGSTS) issued by every thread for exactly the 8 x 4 strip it will consume (no CTA
+//            barrier needed, zero-fill by src-size 0); 8192 LDGSTS per tile go through the same pipe as the sweeps'
+//            shuffles and halo LDS/STS.
+constexpr size_t JS_BAR_OFF = (size_t)2 * 128 * 128 * 4 + sizeof(float4) * 2 * 2 * 16 * 32;    // mbarrier, then a copy of the arguments
+constexpr size_t JS_SMEM = JS_BAR_OFF + 16 + 96;
+
+__device__ __forceinline__ void js_cp_async16_zfill(float* smem_dst, const float* gmem_src, const unsigned src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void js_tma_tile(float* smem_dst, const CUtensorMap* map, const int x, const int y, const int z, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z),
+                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void js_mbar_wait(unsigned long long* bar, const unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+#ifndef SMK_JS_ELEM
+#define SMK_JS_ELEM unsigned long long
+#endif
+typedef SMK_JS_ELEM JsElem;        // strip element of the streaming kernel: a pinned 64-bit pair (see jacobi_core.cuh)
+
+struct JsArgs {
+    const float* pin; float* pout; const float* div;
+    int h, w, pitch; long long bstride;
+    int T, HX, ox, oy, nx, ny, ntot;
+};
+struct JsTile { int bx, by, bz; };
+__device__ __forceinline__ JsTile js_coords(const JsArgs& a, const int t)
+{
+    JsTile c;
+    c.bx = t % a.nx; c.by = (t / a.nx) % a.ny; c.bz = t / (a.nx * a.ny);
+    return c;
+}
+
+// tile c -> shared memory (asynchronously)
+template <bool TMA>
+__device__ __forceinline__ void js_stage(const JsArgs& a, const CUtensorMap* mp, const CUtensorMap* md, float* js_smem, const JsTile c)
+{
+    constexpr int R = 8;
+    float (*sp)[128] = reinterpret_cast<float (*)[128]>(js_smem);                       // staged pressure tile
+    float (*sdv)[128] = reinterpret_cast<float (*)[128]>(js_smem + 128 * 128);            // staged divergence tile
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(js_smem + 2 * 128 * 128 + 4 * 2 * 2 * 16 * 32);
+    const int x0 = c.bx * a.ox, y0 = c.by * a.oy;
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(2u * 128u * 128u * 4u) : "memory");
+            js_tma_tile(&sp[0][0], mp, x0, y0, c.bz, bar);
+            js_tma_tile(&sdv[0][0], md, x0, y0, c.bz, bar);
+        }
+    } else {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const size_t boff = (size_t)c.bz * (size_t)a.bstride;
+        const int gj = x0 + lane * 4, gi0 = y0 + warp * R;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int gi = gi0 + r;
+            const bool ok = gj < a.pitch && gi < a.h;
+            const size_t off = ok ? boff + (size_t)gi * a.pitch + gj : 0;
+            js_cp_async16_zfill(&sp[warp * R + r][4 * lane], a.pin + off, ok ? 16u : 0u);
+            js_cp_async16_zfill(&sdv[warp * R + r][4 * lane], a.div + off, ok ? 16u : 0u);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+}
+
+// One tile: wait for its staged copy, move the thread's strip to registers, start the copy of the next tile, T sweeps,
+// store.  Deliberately NOT inlined into the tile loop, and with 64-bit strip elements: compiled inside the loop with
+// float2 elements, ptxas kept the f32x2 operands in unpaired registers and predicated the ring rows with selects
+// (52 MOV + 36 FSEL per sweep and warp, +37 % instructions: profiles/r01j_*).
+template <int PMASK, bool TMA, bool RING, class E>
+__device__ __noinline__ void js_tile(const JsArgs& a, const CUtensorMap* mp, const CUtensorMap* md, float* js_smem,
+                                     const JsTile c, const JsTile cnext, const bool has_next, const unsigned parity)
+{
+    constexpr int R = 8, NW = 16;
+    float (*sp)[128] = reinterpret_cast<float (*)[128]>(js_smem);
+    float (*sdv)[128] = reinterpret_cast<float (*)[128]>(js_smem + 128 * 128);
+    float4 (*halo)[2][NW][32] = reinterpret_cast<float4 (*)[2][NW][32]>(js_smem + 2 * 128 * 128);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(js_smem + 2 * 128 * 128 + 4 * 2 * 2 * NW * 32);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int T = a.T;
+    const int x0 = c.bx * a.ox, y0 = c.by * a.oy;
+    const int gj = x0 + lane * 4, gi0 = y0 + warp * R;
+
+    if (TMA) js_mbar_wait(bar, parity);
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    PackedStripT<E> A, B, ND;
+    unsigned ringmask = 0;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const float4 pl = *reinterpret_cast<const float4*>(&sp[warp * R + rr][4 * lane]);
+        const float4 ph = *reinterpret_cast<const float4*>(&sp[warp * R + rr + 4][4 * lane]);
+        const float4 dl = *reinterpret_cast<const float4*>(&sdv[warp * R + rr][4 * lane]);
+        const float4 dh = *reinterpret_cast<const float4*>(&sdv[warp * R + rr + 4][4 * lane]);
+        if (RING && (gi0 + rr < 1 || gi0 + rr > a.h - 2)) ringmask |= 1u << rr;
+        if (RING && (gi0 + rr + 4 < 1 || gi0 + rr + 4 > a.h - 2)) ringmask |= 16u << rr;
+        packed_set_rows(A, rr, pl, ph);
+        packed_set_rows(ND, rr, make_float4(-dl.x, -dl.y, -dl.z, -dl.w), make_float4(-dh.x, -dh.y, -dh.z, -dh.w));
+    }
+    E M[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const float m = (gj + cc >= 1 && gj + cc <= a.w - 2) ? 0.25f : 0.f;
+        M[cc] = pe_make<E>(make_float2(m, m));
+    }
+    halo[0][0][warp][lane] = packed_row(A, 0);
+    halo[0][1][warp][lane] = packed_row(A, 7);
+    // the staged strip is in registers (the negations above consumed every load): refill the buffer with the next tile.
+    // LDGSTS: a thread only overwrites its own strip, no barrier needed; the TMA loads overwrite the whole buffer, so they
+    // are issued after the barrier that every thread passes once its strip is read.
+    if (!TMA && has_next) js_stage<false>(a, mp, md, js_smem, cnext);
+    __syncthreads();
+    if (TMA && has_next) js_stage<true>(a, mp, md, js_smem, cnext);
+    int s = 0;
+    for (; s + 1 < T; s += 2) {            // s is even here: sweep s reads halo[0], sweep s+1 reads halo[1]
+        {
+            const float4 up = warp > 0 ? halo[0][1][warp - 1][lane] : zero4;
+            const float4 dn = warp < NW - 1 ? halo[0][0][warp + 1][lane] : zero4;
+            sweep_packed<PMASK, 0, false, 1>(A, B, ND, up, dn, M, ringmask, &halo[1][0][warp][lane], &halo[1][1][warp][lane]);
+            __syncthreads();
+        }
+        {
+            const float4 up = warp > 0 ? halo[1][1][warp - 1][lane] : zero4;
+            const float4 dn = warp < NW - 1 ? halo[1][0][warp + 1][lane] : zero4;
+            const bool more = s + 2 < T;
+            sweep_packed<PMASK, 0, false, 1>(B, A, ND, up, dn, M, ringmask, more ? &halo[0][0][warp][lane] : nullptr, more ? &halo[0][1][warp][lane] : nullptr);
+            if (more) __syncthreads();
+        }
+    }
+    if (s < T) {                           // odd T: one more sweep, then move the result back into A
+        const float4 up = warp > 0 ? halo[0][1][warp - 1][lane] : zero4;
+        const float4 dn = warp < NW - 1 ? halo[0][0][warp + 1][lane] : zero4;
+        sweep_packed<PMASK, 0, false, 1>(A, B, ND, up, dn, M, ringmask, nullptr, nullptr);
+        A = B;
+    }
+
+    const int vx0 = x0 + (c.bx > 0 ? a.HX : 0);
+    const int vx1 = (c.bx + 1 < a.nx) ? x0 + 128 - a.HX : a.pitch;
+    const int vy0 = y0 + (c.by > 0 ? T : 0);
+    const int vy1 = (c.by + 1 < a.ny) ? y0 + NW * R - T : a.h;
+    if (gj >= vx0 && gj < vx1 && gj < a.pitch) {
+        float* out = a.pout + (size_t)c.bz * (size_t)a.bstride;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int gi = gi0 + r;
+            if (gi >= vy0 && gi < vy1 && gi < a.h)
+                *reinterpret_cast<float4*>(out + (size_t)gi * a.pitch + gj) = packed_row(A, r);
+        }
+    }
+    __syncthreads();                       // the halo lines are reused by the next tile
+}
+
+template <int PMASK, bool TMA>
+__global__ void __launch_bounds__(512, 1)
+k_jacobi_stream(const __grid_constant__ JsArgs ga, const __grid_constant__ CUtensorMap mp, const __grid_constant__ CUtensorMap md)
+{
+    extern __shared__ __align__(128) float js_smem[];
+    static_assert(sizeof(JsArgs) <= 96, "JS_SMEM reserves 96 bytes for the argument copy");
+    // js_tile is a separate function: it reads the arguments from shared memory (generic loads of the kernel parameters
+    // cost it a long-scoreboard stall per field and tile: 14 % of the samples in profiles/r01k_*)
+    JsArgs& a = *reinterpret_cast<JsArgs*>(reinterpret_cast<char*>(js_smem) + JS_BAR_OFF + 16);
+    if (threadIdx.x == 0) {
+        a = ga;
+        if (TMA) {
+            unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(js_smem) + JS_BAR_OFF);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    int t = blockIdx.x;
+    unsigned parity = 0;
+    if (t >= ga.ntot) return;
+    JsTile c = js_coords(ga, t);
+    js_stage<TMA>(ga, &mp, &md, js_smem, c);
+    for (; t < ga.ntot; t += gridDim.x, parity ^= 1u) {
+        const bool has_next = t + (int)gridDim.x < ga.ntot;
+        const JsTile cnext = has_next ? js_coords(ga, t + gridDim.x) : c;
+        // tiles in the first / last tile row of a simulation hold rows of the Dirichlet ring (or rows outside the grid);
+        // every other tile runs the sweeps without the ring-row tests
+        const bool ring = c.by == 0 || c.by * ga.oy + 128 > ga.h - 1;
+        if (ring) js_tile<PMASK, TMA, true, JsElem>(a, &mp, &md, js_smem, c, cnext, has_next, parity);
+        else      js_tile<PMASK, TMA, false, JsElem>(a, &mp, &md, js_smem, c, cnext, has_next, parity);
+        c = cnext;
+    }
+}
+
 static int ntiles(int n, int tile, int halo)
 {
     // first tile starts at 0, tiles advance by tile-2*halo, last tile must reach n
@@ -212,6 +421,77 @@ static int use_packed()
     return v;
 }
 
+static int sm_count();
+
+// streaming kernel: opt-in with SMK_JACOBI_STREAM = 1 (LDGSTS staging) / 2 (TMA staging); returns the staging mode or 0.
+// Measured on B200 (tools/tune_jacobi_stream.py, K = 20, T = 10): 8192^2 650 us (TMA) / 735 us (LDGSTS) against 640 us for
+// the two-CTAs-per-SM kernel, 4096^2 189 / 211 against 177 us -- on par at best, so it is not the default yet: a tile
+// still costs 3.0 us on top of its sweeps (0.50 us each).
+static int use_stream(const long ctas)
+{
+    (void)ctas;
+    if (const char* e = getenv("SMK_JACOBI_STREAM")) return use_packed() != 0 ? atoi(e) : 0;
+    return 0;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (nothing of libcuda is linked)
+typedef CUresult (*js_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static js_encode_fn js_encoder()
+{
+    static js_encode_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (js_encode_fn)p;
+    }
+    return fn;
+}
+// a (pitch, h, batch) fp32 tensor read in 128 x 128 x 1 boxes; elements outside it are zero-filled
+static int js_make_map(CUtensorMap* m, const smk_grid_t* g, const float* base)
+{
+    js_encode_fn enc = js_encoder();
+    if (!enc) return fail(SMK_EUNSUPPORTED, "k_jacobi_stream: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)g->pitch_c, (cuuint64_t)g->h, (cuuint64_t)g->batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)g->pitch_c * 4u, (cuuint64_t)g->stride_c * 4u};
+    const cuuint32_t box[3] = {128, 128, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SMK_EINVAL, "k_jacobi_stream: cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d grid", (int)r, g->batch, g->h, g->pitch_c);
+    return SMK_OK;
+}
+
+static int launch_stream(const smk_grid_t* g, const float* src, float* dst, const float* div, int t, int HX, int nx, int ny, int mode, cudaStream_t s)
+{
+    static bool attr_set[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 63;
+    if (!attr_set[dev] || dev == 63) {
+        cudaError_t e = cudaFuncSetAttribute(k_jacobi_stream<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JS_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_jacobi_stream<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JS_SMEM);
+        if (e != cudaSuccess) return fail((int)e, "k_jacobi_stream: cannot opt in to %zu B of shared memory: %s", JS_SMEM, cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    const long ntot = (long)nx * ny * g->batch;
+    const int ctas = (int)(ntot < sm_count() ? ntot : sm_count());
+    JsArgs a;
+    a.pin = src; a.pout = dst; a.div = div; a.h = g->h; a.w = g->w; a.pitch = g->pitch_c; a.bstride = (long long)g->stride_c;
+    a.T = t; a.HX = HX; a.ox = 128 - 2 * HX; a.oy = 128 - 2 * t; a.nx = nx; a.ny = ny; a.ntot = (int)ntot;
+    CUtensorMap mp, md;
+    memset(&mp, 0, sizeof mp); memset(&md, 0, sizeof md);
+    if (mode != 1) {
+        int rc = js_make_map(&mp, g, src);
+        if (rc == SMK_OK) rc = js_make_map(&md, g, div);
+        if (rc != SMK_OK) return rc;
+    }
+    ProfScope prof_(SMK_PH_JACOBI, s);
+    if (mode == 1) k_jacobi_stream<6, false><<<ctas, 512, JS_SMEM, s>>>(a, mp, md);
+    else           k_jacobi_stream<6, true><<<ctas, 512, JS_SMEM, s>>>(a, mp, md);
+    return check_launch("k_jacobi_stream");
+}
+
 template <int R, int NW>
 static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, int K, int T, int* in_scratch, cudaStream_t s)
 {
@@ -227,6 +507,14 @@ static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, in
         const int nx = ntiles(g->w, 128, HX), ny = ntiles(g->h, TH, t);
         dim3 grid(nx, ny, g->batch);
         int rc;
+        int stream_mode = (R == 8 && NW == 16) ? use_stream((long)nx * ny * g->batch) : 0;
+        if (stream_mode == 2 && (g->pitch_c < 128 || g->h < 128)) stream_mode = 1;      // the TMA box is 128 x 128: keep it inside the tensor
+        if (stream_mode) {
+            rc = launch_stream(g, src, dst, div, t, HX, nx, ny, stream_mode, s);
+            if (rc != SMK_OK) return rc;
+            float* tmp = src; src = dst; dst = tmp;
+            continue;
+        }
         {
             ProfScope prof_(SMK_PH_JACOBI, s);
 #define SMK_PACKED_CASE(M) case M: k_jacobi_packed<8, NW, M><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c, \
@@ -274,9 +562,11 @@ int launch_jacobi(const smk_grid_t* g, const float* div, float* p, float* scratc
         // Many waves of CTAs (>= 4 per SM: 4096^2, or a 1/8 slab of 8192^2): 64 x 128 tiles at two CTAs per SM, so that one CTA's tile load / store overlaps
         // the other's sweeps: 7-8 % faster than 128 x 128 tiles at 4096^2 and 8192^2, equal at 2048^2 (tools/tune_jacobi.py).
         const long ctas128 = (long)ntiles(g->w, 128, 12) * ntiles(g->h, 128, 10) * g->batch;
-        if (ctas128 >= 4L * sm_count()) tile = 1;
+        if (use_stream(ctas128)) tile = 2;                  // persistent 128 x 128 CTAs with the next tile prefetched (k_jacobi_stream)
+        else if (ctas128 >= 4L * sm_count()) tile = 1;
     }
     if (T <= 0) T = (tile == 1 || tile == 3) ? 10 : pick_T(g, K, 128, 24, sm_count());
+    if (tile == 2 && T > 12 && use_stream((long)ntiles(g->w, 128, 12) * ntiles(g->h, 128, 10) * g->batch)) T = 10;
     if (tile == 1) return run_cfg<8, 8>(g, div, p, scratch, K, min(T, 12), in_scratch, s);
     if (tile == 3) return run_cfg<4, 16>(g, div, p, scratch, K, min(T, 12), in_scratch, s);
     return run_cfg<8, 16>(g, div, p, scratch, K, min(T, 24), in_scratch, s);

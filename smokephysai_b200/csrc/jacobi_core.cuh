@@ -59,68 +59,132 @@ __device__ __forceinline__ void sweep_rows(float4 (&P)[R], const float4 (&D)[R],
 // another pair (rows rr-1, rr+3 and rr+1, rr+5); only the first add of the two seam row pairs (rows 0|4 and
 // 3|7) is done with scalar adds.  x - div is x + (-div): the divergence is held negated.  A sweep reads one
 // register set and writes another (ping-pong), so no copies are needed to keep the old values alive.
-struct PackedStrip {
-    float2 q[4][4];            // q[rr][c] = (p[rr][c], p[rr + 4][c])
+// The element type E of a strip is float2, or a 64-bit register holding the same pair (PackedStrip64): with float2 the
+// register allocator is free to keep the two halves anywhere and builds an aligned pair in front of every f32x2
+// instruction when it decides on the row-major (float4) layout of the loads and stores -- k_jacobi_stream compiled to
+// 52 MOVs per sweep and warp that way (profiles/r01j_*); a 64-bit element pins the pair, and taking a half out of it
+// (mov.b64 {lo, hi}) costs no instruction.
+template <class E>
+struct PackedStripT {
+    E q[4][4];                 // q[rr][c] = (p[rr][c], p[rr + 4][c])
 };
+using PackedStrip = PackedStripT<float2>;
+using PackedStrip64 = PackedStripT<unsigned long long>;
 
-__device__ __forceinline__ float4 packed_row(const PackedStrip& S, const int r)      // r is a compile-time constant after unrolling
+__device__ __forceinline__ float2 pe_get(const float2 e) { return e; }
+__device__ __forceinline__ float2 pe_get(const unsigned long long e)
 {
-    const int rr = r & 3;
-    return (r < 4) ? make_float4(S.q[rr][0].x, S.q[rr][1].x, S.q[rr][2].x, S.q[rr][3].x)
-                   : make_float4(S.q[rr][0].y, S.q[rr][1].y, S.q[rr][2].y, S.q[rr][3].y);
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(e));
+    return r;
 }
-__device__ __forceinline__ void packed_set_row(PackedStrip& S, const int r, const float4 v)
+__device__ __forceinline__ void pe_set(float2& e, const float2 v) { e = v; }
+__device__ __forceinline__ void pe_set(unsigned long long& e, const float2 v) { asm("mov.b64 %0, {%1, %2};" : "=l"(e) : "f"(v.x), "f"(v.y)); }
+__device__ __forceinline__ float2 pe_add(const float2 a, const float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ unsigned long long pe_add(const unsigned long long a, const unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float2 pe_mul(const float2 a, const float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ unsigned long long pe_mul(const unsigned long long a, const unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+template <class E> __device__ __forceinline__ E pe_make(const float2 v) { E e; pe_set(e, v); return e; }
+
+template <class E>
+__device__ __forceinline__ float4 packed_row(const PackedStripT<E>& S, const int r)      // r is a compile-time constant after unrolling
 {
     const int rr = r & 3;
-    if (r < 4) { S.q[rr][0].x = v.x; S.q[rr][1].x = v.y; S.q[rr][2].x = v.z; S.q[rr][3].x = v.w; }
-    else       { S.q[rr][0].y = v.x; S.q[rr][1].y = v.y; S.q[rr][2].y = v.z; S.q[rr][3].y = v.w; }
+    const float2 a = pe_get(S.q[rr][0]), b = pe_get(S.q[rr][1]), c = pe_get(S.q[rr][2]), d = pe_get(S.q[rr][3]);
+    return (r < 4) ? make_float4(a.x, b.x, c.x, d.x) : make_float4(a.y, b.y, c.y, d.y);
+}
+template <class E>
+__device__ __forceinline__ void packed_set_row(PackedStripT<E>& S, const int r, const float4 v)
+{
+    const int rr = r & 3;
+    const float in[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float2 e = pe_get(S.q[rr][c]);
+        if (r < 4) e.x = in[c]; else e.y = in[c];
+        pe_set(S.q[rr][c], e);
+    }
+}
+
+// rows rr and rr + 4 at once (no read of the old element: usable on an uninitialised strip)
+template <class E>
+__device__ __forceinline__ void packed_set_rows(PackedStripT<E>& S, const int rr, const float4 lo, const float4 hi)
+{
+    pe_set(S.q[rr][0], make_float2(lo.x, hi.x)); pe_set(S.q[rr][1], make_float2(lo.y, hi.y));
+    pe_set(S.q[rr][2], make_float2(lo.z, hi.z)); pe_set(S.q[rr][3], make_float2(lo.w, hi.w));
 }
 
 // one row pair of a sweep: Dst.q[RR] from the old strip S.  PACKED selects f32x2 arithmetic for this pair; with
 // PACKED false the same operations are issued as scalar FADD / FMUL (the two forms run on different issue /
 // pipe resources, so a mix of packed and scalar row pairs is faster than either alone: PMASK in sweep_packed).
-template <int RR, bool PACKED, int DBG = 0>
-__device__ __forceinline__ void packed_pair(const PackedStrip& S, PackedStrip& Dst, const PackedStrip& ND,
-                                            const float4 uph, const float4 dnh, const float2 (&M)[4])
+template <int RR, bool PACKED, int DBG = 0, class E>
+__device__ __forceinline__ void packed_pair(const PackedStripT<E>& S, PackedStripT<E>& Dst, const PackedStripT<E>& ND,
+                                            const float4 uph, const float4 dnh, const E (&M)[4])
 {
     const float uh[4] = {uph.x, uph.y, uph.z, uph.w}, dh[4] = {dnh.x, dnh.y, dnh.z, dnh.w};
     float2 left, right;
-    if (DBG & 1) { left = S.q[RR][3]; right = S.q[RR][0]; }          // probe builds only (tools/micro/jacobi_probe.cu)
+    if (DBG & 1) { left = pe_get(S.q[RR][3]); right = pe_get(S.q[RR][0]); }          // probe builds only (tools/micro/jacobi_probe.cu)
     else {
-        left.x = __shfl_up_sync(0xffffffffu, S.q[RR][3].x, 1);
-        left.y = __shfl_up_sync(0xffffffffu, S.q[RR][3].y, 1);
-        right.x = __shfl_down_sync(0xffffffffu, S.q[RR][0].x, 1);
-        right.y = __shfl_down_sync(0xffffffffu, S.q[RR][0].y, 1);
+        const float2 s3 = pe_get(S.q[RR][3]), s0 = pe_get(S.q[RR][0]);
+        left.x = __shfl_up_sync(0xffffffffu, s3.x, 1);
+        left.y = __shfl_up_sync(0xffffffffu, s3.y, 1);
+        right.x = __shfl_down_sync(0xffffffffu, s0.x, 1);
+        right.y = __shfl_down_sync(0xffffffffu, s0.y, 1);
     }
     if (DBG & 8) {
-        Dst.q[RR][0] = left; Dst.q[RR][3] = right; Dst.q[RR][1] = make_float2(uh[1], dh[1]); Dst.q[RR][2] = make_float2(uh[2], dh[2]);
+        pe_set(Dst.q[RR][0], left); pe_set(Dst.q[RR][3], right);
+        pe_set(Dst.q[RR][1], make_float2(uh[1], dh[1])); pe_set(Dst.q[RR][2], make_float2(uh[2], dh[2]));
         return;
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         float2 t;
-        if (RR == 0)      { t.x = uh[c] + S.q[1][c].x;        t.y = S.q[3][c].x + S.q[1][c].y; }     // rows 0 | 4: up = halo | row 3
-        else if (RR == 3) { t.x = S.q[2][c].x + S.q[0][c].y;  t.y = S.q[2][c].y + dh[c]; }           // rows 3 | 7: down = row 4 | halo
-        else if (PACKED) t = __fadd2_rn(S.q[RR - 1][c], S.q[RR + 1][c]);
-        else { t.x = S.q[RR - 1][c].x + S.q[RR + 1][c].x; t.y = S.q[RR - 1][c].y + S.q[RR + 1][c].y; }
-        const float2 l = (c == 0) ? left : S.q[RR][c - 1];
-        const float2 r = (c == 3) ? right : S.q[RR][c + 1];
+        E te;
+        if (RR == 0) {                                                                                // rows 0 | 4: up = halo | row 3
+            const float2 a = pe_get(S.q[1][c]), b = pe_get(S.q[3][c]);
+            t.x = uh[c] + a.x; t.y = b.x + a.y;
+            if (PACKED) te = pe_make<E>(t);
+        } else if (RR == 3) {                                                                         // rows 3 | 7: down = row 4 | halo
+            const float2 a = pe_get(S.q[2][c]), b = pe_get(S.q[0][c]);
+            t.x = a.x + b.y; t.y = a.y + dh[c];
+            if (PACKED) te = pe_make<E>(t);
+        } else if (PACKED) te = pe_add(S.q[RR - 1][c], S.q[RR + 1][c]);
+        else {
+            const float2 a = pe_get(S.q[RR - 1][c]), b = pe_get(S.q[RR + 1][c]);
+            t.x = a.x + b.x; t.y = a.y + b.y;
+        }
         if (PACKED) {
-            t = __fadd2_rn(t, l);
-            t = __fadd2_rn(t, r);
-            t = __fadd2_rn(t, ND.q[RR][c]);
-            Dst.q[RR][c] = __fmul2_rn(M[c], t);
+            const E l = (c == 0) ? pe_make<E>(left) : S.q[RR][c - 1];
+            const E r = (c == 3) ? pe_make<E>(right) : S.q[RR][c + 1];
+            te = pe_add(te, l);
+            te = pe_add(te, r);
+            te = pe_add(te, ND.q[RR][c]);
+            Dst.q[RR][c] = pe_mul(M[c], te);
         } else {
+            const float2 l = (c == 0) ? left : pe_get(S.q[RR][c - 1]);
+            const float2 r = (c == 3) ? right : pe_get(S.q[RR][c + 1]);
+            const float2 nd = pe_get(ND.q[RR][c]), m = pe_get(M[c]);
             t.x = t.x + l.x; t.y = t.y + l.y;
             t.x = t.x + r.x; t.y = t.y + r.y;
-            t.x = t.x + ND.q[RR][c].x; t.y = t.y + ND.q[RR][c].y;
-            Dst.q[RR][c] = make_float2(M[c].x * t.x, M[c].y * t.y);
+            t.x = t.x + nd.x; t.y = t.y + nd.y;
+            pe_set(Dst.q[RR][c], make_float2(m.x * t.x, m.y * t.y));
         }
     }
 }
 
 // rows of the strip that are on the Dirichlet ring or outside the grid: bit r set -> row r is forced to 0
-__device__ __forceinline__ void packed_zero_rows(PackedStrip& S, const unsigned ringmask)
+template <class E>
+__device__ __forceinline__ void packed_zero_rows(PackedStripT<E>& S, const unsigned ringmask)
 {
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -135,9 +199,9 @@ __device__ __forceinline__ void mbar_arrive_cta(unsigned long long* b)
 }
 
 // posted (optional, MBAR builds): an mbarrier every lane arrives on once its two boundary rows are in shared memory
-template <int PMASK, int DBG = 0, bool MBAR = false, int ORDER = 0>
-__device__ __forceinline__ void sweep_packed(const PackedStrip& S, PackedStrip& Dst, const PackedStrip& ND,
-                                             const float4 uph, const float4 dnh, const float2 (&M)[4], const unsigned ringmask,
+template <int PMASK, int DBG = 0, bool MBAR = false, int ORDER = 0, class E>
+__device__ __forceinline__ void sweep_packed(const PackedStripT<E>& S, PackedStripT<E>& Dst, const PackedStripT<E>& ND,
+                                             const float4 uph, const float4 dnh, const E (&M)[4], const unsigned ringmask,
                                              float4* post_first, float4* post_last, unsigned long long* posted = nullptr)
 {
     // ORDER 0: boundary pairs, post, interior pairs;  1: interior pairs, boundary pairs, post;  2: pair 1, boundary pairs,

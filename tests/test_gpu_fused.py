@@ -127,6 +127,38 @@ def test_fused_multi_step_launch_equals_single_steps(h, w):
         assert not full[:, :, cols:].any(), "padding of %s" % name
 
 
+@pytest.mark.parametrize("h,w,B,n,seg", [(128, 128, 5, 7, 3), (128, 128, 5, 7, 9), (128, 128, 4, 6, 1), (60, 128, 6, 5, 4), (128, 52, 3, 8, 5),
+                                         (128, 128, 7, 4, 28)])
+def test_fused_time_sliced_schedule_equals_one_cta_per_simulation(h, w, B, n, seg, monkeypatch):
+    """The time-sliced schedule of k_step_fused (a CTA runs `seg` consecutive simulation-steps of the simulation-major
+    line and hands a simulation cut by its piece boundary over to the next CTA through global memory) must give the
+    frames and fields of the one-CTA-per-simulation schedule bit for bit.  SMK_FUSED_SLICE forces the piece length:
+    seg < n chains a simulation through several CTAs, seg > n packs several simulations into one CTA."""
+    K = 12
+    states = [random_state(h, w, 500 + b, vel=150.0) for b in range(B)]
+    out = {}
+    for mode in ("0", str(seg)):
+        monkeypatch.setenv("SMK_FUSED_SLICE", mode)
+        ns = make(h, w, 0.02, 0.004, K, batch=B, step_kernel="fused")
+        for k in FIELDS:
+            setattr(ns, k, T(np.stack([st[k] for st in states])))
+        fmul = torch.linspace(0.0, 0.05, h * ns._layout.pitch_c, device="cuda").view(h, ns._layout.pitch_c)
+        n0 = _lib.launch_count()
+        frames = ns.run_steps(n, fmul=fmul)
+        assert _lib.launch_count() - n0 == 1
+        out[mode] = (N(frames), {k: N(getattr(ns, k)) for k in FIELDS})
+    assert_same(out[str(seg)][0], out["0"][0], "frames, sliced vs classic")
+    for k in FIELDS:
+        assert_same(out[str(seg)][1][k], out["0"][1][k], k + ", sliced vs classic")
+    ref = oracle.OracleSolver((h, w), 0.02, 0.004, K)
+    for k in FIELDS:
+        setattr(ref, k, states[B - 1][k].copy())
+    for _ in range(n):
+        ref.step()
+    for k in FIELDS:
+        assert_same(out[str(seg)][1][k][B - 1], getattr(ref, k), k + " vs oracle")
+
+
 def test_fused_time_major_frames_and_generate_sequences():
     B, L = 6, 9
     ems = [[((x, y), i) for x, y, _, i in emitters_for_sequence(s)] for s in range(B)]

@@ -390,12 +390,14 @@ def test_abi_rejects_bad_arguments():
         _lib.call("smk_diffuse", st.u[0], st.u[0], 4, 4, 4, 1, 16, 0.1, None)
 
 
-@pytest.mark.parametrize("tile", [1, 2, 3])
-@pytest.mark.parametrize("h,w,K,T_", [(300, 200, 33, 8), (130, 520, 20, 10), (1030, 260, 24, 12)])
+@pytest.mark.parametrize("tile", [1, 2, 3, "stream1", "stream2"])
+@pytest.mark.parametrize("h,w,K,T_", [(300, 200, 33, 8), (130, 520, 20, 10), (1030, 260, 24, 12), (700, 900, 7, 1), (129, 131, 5, 5),
+                                      (1500, 1900, 20, 10)])
 def test_jacobi_every_tile_shape_vs_oracle(tile, h, w, K, T_):
     """The tiled Jacobi picks its CTA tile by grid size (128 x 128 one CTA per SM, 64 x 128 two CTAs per SM for grids of
     many CTA waves); every shape must give the oracle's pressure bit for bit.  SMK_JACOBI_TILE forces the shape."""
-    rng = np.random.default_rng(tile * 100 + h)
+    stream = int(tile[-1]) if isinstance(tile, str) else 0
+    rng = np.random.default_rng((9 if stream else tile) * 100 + h)
     p = rng.standard_normal((h, w)).astype(np.float32)
     div = rng.standard_normal((h, w)).astype(np.float32)
     ns = make(h, w, K=K, sweeps_per_launch=T_)
@@ -403,17 +405,51 @@ def test_jacobi_every_tile_shape_vs_oracle(tile, h, w, K, T_):
     ns._field("div").copy_(T(div))
     st = ns._state
     flag = C.c_int32(0)
-    old = os.environ.get("SMK_JACOBI_TILE")
-    os.environ["SMK_JACOBI_TILE"] = str(tile)
+    saved = {k: os.environ.get(k) for k in ("SMK_JACOBI_TILE", "SMK_JACOBI_STREAM")}
+    # "stream1/2": the persistent kernel that prefetches the next 128 x 128 tile into shared memory with 16-byte cp.async (1) or
+    # with two TMA tensor loads completed on an mbarrier (2); 1500 x 1900 gives its CTAs two tiles each, the others one or none
+    os.environ["SMK_JACOBI_TILE"] = "2" if stream else str(tile)
+    os.environ["SMK_JACOBI_STREAM"] = str(stream)
     try:
         _lib.call("smk_jacobi", C.byref(ns._grid), st.div, st.p[0], st.p[1], K, T_, C.byref(flag), ns._stream())
     finally:
-        if old is None:
-            del os.environ["SMK_JACOBI_TILE"]
-        else:
-            os.environ["SMK_JACOBI_TILE"] = old
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     st.cur_p = flag.value
-    assert_same(N(ns.p), oracle.jacobi(p, div, K), "jacobi tile %d" % tile)
+    assert_same(N(ns.p), oracle.jacobi(p, div, K), "jacobi tile %s" % tile)
+
+
+@pytest.mark.parametrize("stream", [1, 2])
+def test_jacobi_stream_batched_vs_oracle(stream):
+    """The streaming kernel's tile index runs over (batch, tile row, tile column): 40 simulations of 300 x 260 are 360 tiles,
+    so every CTA walks across simulation boundaries."""
+    h, w, K, B = 300, 260, 12, 40
+    rng = np.random.default_rng(77 + stream)
+    p = rng.standard_normal((B, h, w)).astype(np.float32)
+    div = rng.standard_normal((B, h, w)).astype(np.float32)
+    ns = make(h, w, K=K, sweeps_per_launch=6, batch=B)
+    ns.p = T(p)
+    ns._field("div").copy_(T(div))
+    st = ns._state
+    flag = C.c_int32(0)
+    saved = {k: os.environ.get(k) for k in ("SMK_JACOBI_TILE", "SMK_JACOBI_STREAM")}
+    os.environ["SMK_JACOBI_TILE"] = "2"
+    os.environ["SMK_JACOBI_STREAM"] = str(stream)
+    try:
+        _lib.call("smk_jacobi", C.byref(ns._grid), st.div, st.p[0], st.p[1], K, 6, C.byref(flag), ns._stream())
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    st.cur_p = flag.value
+    got = N(ns.p)
+    for b in range(B):
+        assert_same(got[b], oracle.jacobi(p[b], div[b], K), "jacobi stream %d, simulation %d" % (stream, b))
 
 
 @pytest.fixture
