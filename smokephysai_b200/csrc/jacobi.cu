@@ -184,8 +184,9 @@ k_jacobi_packed(const float* __restrict__ pin, float* __restrict__ pout, const f
 //   !TMA  -- 16-byte cp.async (LDGSTS) issued by every thread for exactly the 8 x 4 strip it will consume (no CTA
 //            barrier needed, zero-fill by src-size 0); 8192 LDGSTS per tile go through the same pipe as the sweeps'
 //            shuffles and halo LDS/STS.
-constexpr size_t JS_BAR_OFF = (size_t)2 * 128 * 128 * 4 + sizeof(float4) * 2 * 2 * 16 * 32;    // mbarrier, then a copy of the arguments
-constexpr size_t JS_SMEM = JS_BAR_OFF + 16 + 96;
+// shared memory of a CTA of NW warps (tile = 8 NW x 128): staged pressure, staged divergence, halo lines, mbarrier, arguments
+__host__ __device__ constexpr size_t js_bar_off(const int NW) { return (size_t)2 * 8 * NW * 128 * 4 + sizeof(float4) * 2 * 2 * NW * 32; }
+__host__ __device__ constexpr size_t js_smem_bytes(const int NW) { return js_bar_off(NW) + 16 + 96; }
 
 __device__ __forceinline__ void js_cp_async16_zfill(float* smem_dst, const float* gmem_src, const unsigned src_bytes)
 {
@@ -224,18 +225,18 @@ __device__ __forceinline__ JsTile js_coords(const JsArgs& a, const int t)
 }
 
 // tile c -> shared memory (asynchronously)
-template <bool TMA>
+template <bool TMA, int NW>
 __device__ __forceinline__ void js_stage(const JsArgs& a, const CUtensorMap* mp, const CUtensorMap* md, float* js_smem, const JsTile c)
 {
-    constexpr int R = 8;
+    constexpr int R = 8, TH = R * NW;
     float (*sp)[128] = reinterpret_cast<float (*)[128]>(js_smem);                       // staged pressure tile
-    float (*sdv)[128] = reinterpret_cast<float (*)[128]>(js_smem + 128 * 128);            // staged divergence tile
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(js_smem + 2 * 128 * 128 + 4 * 2 * 2 * 16 * 32);
+    float (*sdv)[128] = reinterpret_cast<float (*)[128]>(js_smem + TH * 128);             // staged divergence tile
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(js_smem) + js_bar_off(NW));
     const int x0 = c.bx * a.ox, y0 = c.by * a.oy;
     if (TMA) {
         if (threadIdx.x == 0) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                         :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(2u * 128u * 128u * 4u) : "memory");
+                         :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(2u * (unsigned)TH * 128u * 4u) : "memory");
             js_tma_tile(&sp[0][0], mp, x0, y0, c.bz, bar);
             js_tma_tile(&sdv[0][0], md, x0, y0, c.bz, bar);
         }
@@ -259,15 +260,15 @@ __device__ __forceinline__ void js_stage(const JsArgs& a, const CUtensorMap* mp,
 // store.  Deliberately NOT inlined into the tile loop, and with 64-bit strip elements: compiled inside the loop with
 // float2 elements, ptxas kept the f32x2 operands in unpaired registers and predicated the ring rows with selects
 // (52 MOV + 36 FSEL per sweep and warp, +37 % instructions: profiles/r01j_*).
-template <int PMASK, bool TMA, bool RING, class E>
+template <int PMASK, bool TMA, bool RING, class E, int NW>
 __device__ __noinline__ void js_tile(const JsArgs& a, const CUtensorMap* mp, const CUtensorMap* md, float* js_smem,
                                      const JsTile c, const JsTile cnext, const bool has_next, const unsigned parity)
 {
-    constexpr int R = 8, NW = 16;
+    constexpr int R = 8, TH = R * NW;
     float (*sp)[128] = reinterpret_cast<float (*)[128]>(js_smem);
-    float (*sdv)[128] = reinterpret_cast<float (*)[128]>(js_smem + 128 * 128);
-    float4 (*halo)[2][NW][32] = reinterpret_cast<float4 (*)[2][NW][32]>(js_smem + 2 * 128 * 128);
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(js_smem + 2 * 128 * 128 + 4 * 2 * 2 * NW * 32);
+    float (*sdv)[128] = reinterpret_cast<float (*)[128]>(js_smem + TH * 128);
+    float4 (*halo)[2][NW][32] = reinterpret_cast<float4 (*)[2][NW][32]>(js_smem + 2 * TH * 128);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(js_smem) + js_bar_off(NW));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int T = a.T;
@@ -300,9 +301,9 @@ __device__ __noinline__ void js_tile(const JsArgs& a, const CUtensorMap* mp, con
     // the staged strip is in registers (the negations above consumed every load): refill the buffer with the next tile.
     // LDGSTS: a thread only overwrites its own strip, no barrier needed; the TMA loads overwrite the whole buffer, so they
     // are issued after the barrier that every thread passes once its strip is read.
-    if (!TMA && has_next) js_stage<false>(a, mp, md, js_smem, cnext);
+    if (!TMA && has_next) js_stage<false, NW>(a, mp, md, js_smem, cnext);
     __syncthreads();
-    if (TMA && has_next) js_stage<true>(a, mp, md, js_smem, cnext);
+    if (TMA && has_next) js_stage<true, NW>(a, mp, md, js_smem, cnext);
     int s = 0;
     for (; s + 1 < T; s += 2) {            // s is even here: sweep s reads halo[0], sweep s+1 reads halo[1]
         {
@@ -342,19 +343,19 @@ __device__ __noinline__ void js_tile(const JsArgs& a, const CUtensorMap* mp, con
     __syncthreads();                       // the halo lines are reused by the next tile
 }
 
-template <int PMASK, bool TMA>
-__global__ void __launch_bounds__(512, 1)
+template <int PMASK, bool TMA, int NW>
+__global__ void __launch_bounds__(NW * 32, (NW * 32 <= 256) ? 2 : 1)
 k_jacobi_stream(const __grid_constant__ JsArgs ga, const __grid_constant__ CUtensorMap mp, const __grid_constant__ CUtensorMap md)
 {
     extern __shared__ __align__(128) float js_smem[];
-    static_assert(sizeof(JsArgs) <= 96, "JS_SMEM reserves 96 bytes for the argument copy");
+    static_assert(sizeof(JsArgs) <= 96, "js_smem_bytes reserves 96 bytes for the argument copy");
     // js_tile is a separate function: it reads the arguments from shared memory (generic loads of the kernel parameters
     // cost it a long-scoreboard stall per field and tile: 14 % of the samples in profiles/r01k_*)
-    JsArgs& a = *reinterpret_cast<JsArgs*>(reinterpret_cast<char*>(js_smem) + JS_BAR_OFF + 16);
+    JsArgs& a = *reinterpret_cast<JsArgs*>(reinterpret_cast<char*>(js_smem) + js_bar_off(NW) + 16);
     if (threadIdx.x == 0) {
         a = ga;
         if (TMA) {
-            unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(js_smem) + JS_BAR_OFF);
+            unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(js_smem) + js_bar_off(NW));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -364,15 +365,15 @@ k_jacobi_stream(const __grid_constant__ JsArgs ga, const __grid_constant__ CUten
     unsigned parity = 0;
     if (t >= ga.ntot) return;
     JsTile c = js_coords(ga, t);
-    js_stage<TMA>(ga, &mp, &md, js_smem, c);
+    js_stage<TMA, NW>(ga, &mp, &md, js_smem, c);
     for (; t < ga.ntot; t += gridDim.x, parity ^= 1u) {
         const bool has_next = t + (int)gridDim.x < ga.ntot;
         const JsTile cnext = has_next ? js_coords(ga, t + gridDim.x) : c;
         // tiles in the first / last tile row of a simulation hold rows of the Dirichlet ring (or rows outside the grid);
         // every other tile runs the sweeps without the ring-row tests
-        const bool ring = c.by == 0 || c.by * ga.oy + 128 > ga.h - 1;
-        if (ring) js_tile<PMASK, TMA, true, JsElem>(a, &mp, &md, js_smem, c, cnext, has_next, parity);
-        else      js_tile<PMASK, TMA, false, JsElem>(a, &mp, &md, js_smem, c, cnext, has_next, parity);
+        const bool ring = c.by == 0 || c.by * ga.oy + 8 * NW > ga.h - 1;
+        if (ring) js_tile<PMASK, TMA, true, JsElem, NW>(a, &mp, &md, js_smem, c, cnext, has_next, parity);
+        else      js_tile<PMASK, TMA, false, JsElem, NW>(a, &mp, &md, js_smem, c, cnext, has_next, parity);
         c = cnext;
     }
 }
@@ -423,15 +424,18 @@ static int use_packed()
 
 static int sm_count();
 
-// streaming kernel: opt-in with SMK_JACOBI_STREAM = 1 (LDGSTS staging) / 2 (TMA staging); returns the staging mode or 0.
-// Measured on B200 (tools/tune_jacobi_stream.py, K = 20, T = 10): 8192^2 650 us (TMA) / 735 us (LDGSTS) against 640 us for
-// the two-CTAs-per-SM kernel, 4096^2 189 / 211 against 177 us -- on par at best, so it is not the default yet: a tile
-// still costs 3.0 us on top of its sweeps (0.50 us each).
-static int use_stream(const long ctas)
+// Streaming kernel: SMK_JACOBI_STREAM = 0 (off) / 1 (LDGSTS staging) / 2 (TMA staging) forces, otherwise launch_jacobi picks it
+// for grids of many CTA waves.  Measured on B200 (tools/tune_jacobi_stream.py, K = 20, T = 10, us per 20 sweeps):
+//                      two CTAs per SM   128 x 128   stream LDGSTS   stream TMA   stream TMA, 64 x 128 x 2
+//   8192 x 8192             644             711          669            576              635
+//   4096 x 4096             178             195          193            168              177
+//   1024 x 8192 (slab)       96             111          110             99               93
+//   2048 x 2048              54              50           58             54               54
+// A tile still costs 2.3 us on top of its sweeps (0.48 us each).
+static int stream_env()
 {
-    (void)ctas;
     if (const char* e = getenv("SMK_JACOBI_STREAM")) return use_packed() != 0 ? atoi(e) : 0;
-    return 0;
+    return -1;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (nothing of libcuda is linked)
@@ -448,14 +452,14 @@ static js_encode_fn js_encoder()
     }
     return fn;
 }
-// a (pitch, h, batch) fp32 tensor read in 128 x 128 x 1 boxes; elements outside it are zero-filled
-static int js_make_map(CUtensorMap* m, const smk_grid_t* g, const float* base)
+// a (pitch, h, batch) fp32 tensor read in 128 x box_rows x 1 boxes; elements outside it are zero-filled
+static int js_make_map(CUtensorMap* m, const smk_grid_t* g, const float* base, const int box_rows)
 {
     js_encode_fn enc = js_encoder();
     if (!enc) return fail(SMK_EUNSUPPORTED, "k_jacobi_stream: cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[3] = {(cuuint64_t)g->pitch_c, (cuuint64_t)g->h, (cuuint64_t)g->batch};
     const cuuint64_t strides[2] = {(cuuint64_t)g->pitch_c * 4u, (cuuint64_t)g->stride_c * 4u};
-    const cuuint32_t box[3] = {128, 128, 1}, estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {128, (cuuint32_t)box_rows, 1}, estr[3] = {1, 1, 1};
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -463,37 +467,41 @@ static int js_make_map(CUtensorMap* m, const smk_grid_t* g, const float* base)
     return SMK_OK;
 }
 
+template <int NW>
 static int launch_stream(const smk_grid_t* g, const float* src, float* dst, const float* div, int t, int HX, int nx, int ny, int mode, cudaStream_t s)
 {
+    constexpr size_t SMEM = js_smem_bytes(NW);
+    constexpr int PER_SM = (NW * 32 <= 256) ? 2 : 1;
     static bool attr_set[64] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 63;
     if (!attr_set[dev] || dev == 63) {
-        cudaError_t e = cudaFuncSetAttribute(k_jacobi_stream<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JS_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_jacobi_stream<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JS_SMEM);
-        if (e != cudaSuccess) return fail((int)e, "k_jacobi_stream: cannot opt in to %zu B of shared memory: %s", JS_SMEM, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(k_jacobi_stream<6, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_jacobi_stream<6, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) return fail((int)e, "k_jacobi_stream: cannot opt in to %zu B of shared memory: %s", SMEM, cudaGetErrorString(e));
         attr_set[dev] = true;
     }
     const long ntot = (long)nx * ny * g->batch;
-    const int ctas = (int)(ntot < sm_count() ? ntot : sm_count());
+    const long resident = (long)PER_SM * sm_count();
+    const int ctas = (int)(ntot < resident ? ntot : resident);
     JsArgs a;
     a.pin = src; a.pout = dst; a.div = div; a.h = g->h; a.w = g->w; a.pitch = g->pitch_c; a.bstride = (long long)g->stride_c;
-    a.T = t; a.HX = HX; a.ox = 128 - 2 * HX; a.oy = 128 - 2 * t; a.nx = nx; a.ny = ny; a.ntot = (int)ntot;
+    a.T = t; a.HX = HX; a.ox = 128 - 2 * HX; a.oy = 8 * NW - 2 * t; a.nx = nx; a.ny = ny; a.ntot = (int)ntot;
     CUtensorMap mp, md;
     memset(&mp, 0, sizeof mp); memset(&md, 0, sizeof md);
     if (mode != 1) {
-        int rc = js_make_map(&mp, g, src);
-        if (rc == SMK_OK) rc = js_make_map(&md, g, div);
+        int rc = js_make_map(&mp, g, src, 8 * NW);
+        if (rc == SMK_OK) rc = js_make_map(&md, g, div, 8 * NW);
         if (rc != SMK_OK) return rc;
     }
     ProfScope prof_(SMK_PH_JACOBI, s);
-    if (mode == 1) k_jacobi_stream<6, false><<<ctas, 512, JS_SMEM, s>>>(a, mp, md);
-    else           k_jacobi_stream<6, true><<<ctas, 512, JS_SMEM, s>>>(a, mp, md);
+    if (mode == 1) k_jacobi_stream<6, false, NW><<<ctas, NW * 32, SMEM, s>>>(a, mp, md);
+    else           k_jacobi_stream<6, true, NW><<<ctas, NW * 32, SMEM, s>>>(a, mp, md);
     return check_launch("k_jacobi_stream");
 }
 
 template <int R, int NW>
-static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, int K, int T, int* in_scratch, cudaStream_t s)
+static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, int K, int T, int* in_scratch, cudaStream_t s, const int stream = 0)
 {
     const int TH = R * NW;
     const bool whole = (g->h <= TH) && (g->w <= 128);
@@ -507,10 +515,10 @@ static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, in
         const int nx = ntiles(g->w, 128, HX), ny = ntiles(g->h, TH, t);
         dim3 grid(nx, ny, g->batch);
         int rc;
-        int stream_mode = (R == 8 && NW == 16) ? use_stream((long)nx * ny * g->batch) : 0;
-        if (stream_mode == 2 && (g->pitch_c < 128 || g->h < 128)) stream_mode = 1;      // the TMA box is 128 x 128: keep it inside the tensor
+        int stream_mode = (R == 8 && (NW == 16 || NW == 8)) ? stream : 0;
+        if (stream_mode == 2 && (g->pitch_c < 128 || g->h < TH)) stream_mode = 1;       // the TMA box is 128 x TH: keep it inside the tensor
         if (stream_mode) {
-            rc = launch_stream(g, src, dst, div, t, HX, nx, ny, stream_mode, s);
+            rc = launch_stream<(R == 8 && NW == 8) ? 8 : 16>(g, src, dst, div, t, HX, nx, ny, stream_mode, s);
             if (rc != SMK_OK) return rc;
             float* tmp = src; src = dst; dst = tmp;
             continue;
@@ -558,18 +566,26 @@ int launch_jacobi(const smk_grid_t* g, const float* div, float* p, float* scratc
     // large grids: overlapped tiles.  T must leave a positive advance in both directions.
     int tile = 0;                                   // 0 auto, 1: 64 x 128 (8 warps), 2: 128 x 128 (16 warps), 3: 64 x 128 (16 warps)
     if (const char* e = getenv("SMK_JACOBI_TILE")) tile = atoi(e);
+    int stream = stream_env();                      // -1 auto, 0 off, 1 LDGSTS, 2 TMA (k_jacobi_stream)
     if (tile == 0) {
-        // Many waves of CTAs (>= 4 per SM: 4096^2, or a 1/8 slab of 8192^2): 64 x 128 tiles at two CTAs per SM, so that one CTA's tile load / store overlaps
-        // the other's sweeps: 7-8 % faster than 128 x 128 tiles at 4096^2 and 8192^2, equal at 2048^2 (tools/tune_jacobi.py).
+        // Many waves of CTAs (>= 4 per SM: 4096^2, or a 1/8 slab of 8192^2): overlap one tile's load / store with another's sweeps.
+        // Without the TMA kernel: 64 x 128 tiles at two CTAs per SM (7-8 % faster than 128 x 128 tiles at 4096^2 and 8192^2, equal
+        // at 2048^2: tools/tune_jacobi.py).  With it: persistent CTAs that prefetch their next tile, 128 x 128 when the grid
+        // has many tile rows (another 6-10 %), 64 x 128 x 2 for slab-shaped grids (table above).
         const long ctas128 = (long)ntiles(g->w, 128, 12) * ntiles(g->h, 128, 10) * g->batch;
-        if (use_stream(ctas128)) tile = 2;                  // persistent 128 x 128 CTAs with the next tile prefetched (k_jacobi_stream)
-        else if (ctas128 >= 4L * sm_count()) tile = 1;
+        if (ctas128 >= 4L * sm_count()) {
+            tile = 1;
+            if (stream < 0 && use_packed() != 0 && g->pitch_c >= 128 && js_encoder() != nullptr) {
+                stream = 2;
+                if (ntiles(g->h, 128, 10) >= 16) tile = 2;
+            }
+        }
     }
-    if (T <= 0) T = (tile == 1 || tile == 3) ? 10 : pick_T(g, K, 128, 24, sm_count());
-    if (tile == 2 && T > 12 && use_stream((long)ntiles(g->w, 128, 12) * ntiles(g->h, 128, 10) * g->batch)) T = 10;
-    if (tile == 1) return run_cfg<8, 8>(g, div, p, scratch, K, min(T, 12), in_scratch, s);
+    if (stream < 0) stream = 0;
+    if (T <= 0) T = (tile == 1 || tile == 3 || stream != 0) ? 10 : pick_T(g, K, 128, 24, sm_count());
+    if (tile == 1) return run_cfg<8, 8>(g, div, p, scratch, K, min(T, 12), in_scratch, s, stream);
     if (tile == 3) return run_cfg<4, 16>(g, div, p, scratch, K, min(T, 12), in_scratch, s);
-    return run_cfg<8, 16>(g, div, p, scratch, K, min(T, 24), in_scratch, s);
+    return run_cfg<8, 16>(g, div, p, scratch, K, min(T, stream != 0 ? 12 : 24), in_scratch, s, stream);
 }
 
 }  // namespace smk

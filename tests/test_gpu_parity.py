@@ -390,7 +390,7 @@ def test_abi_rejects_bad_arguments():
         _lib.call("smk_diffuse", st.u[0], st.u[0], 4, 4, 4, 1, 16, 0.1, None)
 
 
-@pytest.mark.parametrize("tile", [1, 2, 3, "stream1", "stream2"])
+@pytest.mark.parametrize("tile", [1, 2, 3, "stream1", "stream2", "half-stream1", "half-stream2"])
 @pytest.mark.parametrize("h,w,K,T_", [(300, 200, 33, 8), (130, 520, 20, 10), (1030, 260, 24, 12), (700, 900, 7, 1), (129, 131, 5, 5),
                                       (1500, 1900, 20, 10)])
 def test_jacobi_every_tile_shape_vs_oracle(tile, h, w, K, T_):
@@ -408,7 +408,8 @@ def test_jacobi_every_tile_shape_vs_oracle(tile, h, w, K, T_):
     saved = {k: os.environ.get(k) for k in ("SMK_JACOBI_TILE", "SMK_JACOBI_STREAM")}
     # "stream1/2": the persistent kernel that prefetches the next 128 x 128 tile into shared memory with 16-byte cp.async (1) or
     # with two TMA tensor loads completed on an mbarrier (2); 1500 x 1900 gives its CTAs two tiles each, the others one or none
-    os.environ["SMK_JACOBI_TILE"] = "2" if stream else str(tile)
+    # "half-stream1/2": the same kernel on 64 x 128 tiles, two persistent CTAs per SM
+    os.environ["SMK_JACOBI_TILE"] = ("1" if tile.startswith("half") else "2") if stream else str(tile)
     os.environ["SMK_JACOBI_STREAM"] = str(stream)
     try:
         _lib.call("smk_jacobi", C.byref(ns._grid), st.div, st.p[0], st.p[1], K, T_, C.byref(flag), ns._stream())

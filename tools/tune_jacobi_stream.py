@@ -17,7 +17,7 @@ ns._field("div").copy_(torch.randn(ns._field("div").shape, device="cuda"))
 st = ns._state
 flag = C.c_int32(0)
 for name, tile, stream, Ts in (("64x128 x2", 1, 0, (10,)), ("128x128", 2, 0, (10,)), ("stream ldgsts", 2, 1, (10,)),
-                               ("stream tma", 2, 2, (5, 8, 10, 12))):
+                               ("stream tma", 2, 2, (5, 8, 10, 12)), ("stream tma x2", 1, 2, (5, 8, 10)), ("stream ldgsts x2", 1, 1, (10,))):
     os.environ["SMK_JACOBI_TILE"] = str(tile)
     os.environ["SMK_JACOBI_STREAM"] = str(stream)
     for T in Ts:
@@ -34,4 +34,4 @@ for name, tile, stream, Ts in (("64x128 x2", 1, 0, (10,)), ("128x128", 2, 0, (10
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
-        print("%dx%d K %d  %-14s T %2d: %8.1f us, %7.1f G cell-sweeps/s" % (h, w, K, name, T, ms * 1e3, batch * h * w * K / ms / 1e6), flush=True)
+        print("%dx%d K %d  %-16s T %2d: %8.1f us, %7.1f G cell-sweeps/s" % (h, w, K, name, T, ms * 1e3, batch * h * w * K / ms / 1e6), flush=True)
