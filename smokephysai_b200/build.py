@@ -42,7 +42,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return SO
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("SMK_NVCC_EXTRA", "").split()          # e.g. -DSMK_FZ_ELEM=float2 for an A/B build of a kernel variant
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd))

@@ -35,6 +35,13 @@ constexpr int FZ_PMASK = SMK_FZ_PMASK;   // bit rr: row pair rr of a sweep uses 
 #define SMK_FZ_INTERIOR_FIRST 1
 #endif
 constexpr int FZ_ORDER = SMK_FZ_INTERIOR_FIRST;   // a sweep computes rows 1..6 before rows 0 and 7 (hides the halo loads): mask 6 + this order is 2.3 % faster on c2 than mask 7 + boundary rows first
+#ifndef SMK_FZ_ELEM
+#define SMK_FZ_ELEM float2
+#endif
+// element of the pressure strips (jacobi_core.cuh): float2, or a pinned 64-bit pair.  The 64-bit element removes 6 % of the
+// sweep loop's instructions here (no FSEL, fewer MOV) but c2 ran 2 % slower with it (49.1 against 50.1 G cell-steps/s), so float2 stays.
+typedef SMK_FZ_ELEM FzElem;
+typedef PackedStripT<FzElem> FzStrip;
 constexpr size_t FZ_SMEM = (size_t)(FZ_SU + FZ_SV + FZ_SD) * 4 + sizeof(float4) * 2 * 2 * FZ_NW * 32;
 
 // Phase timing for tools/micro/fused_probe.cu only (never defined in the library build): thread 0 of CTA 0
@@ -294,7 +301,7 @@ k_step_fused(const FusedArgs a)
         }
     }
     // pressure: the packed register strip of jacobi_core.cuh (a float2 pairs row r with row r + 4)
-    PackedStrip P;
+    FzStrip P = {};
     const bool colin = c0 < pc;
     unsigned ringmask = 0;              // rows of the strip on the Dirichlet ring or outside the grid
 #pragma unroll
@@ -303,11 +310,11 @@ k_step_fused(const FusedArgs a)
         packed_set_row(P, r, (colin && i < h) ? __ldcg(reinterpret_cast<const float4*>(gP + (size_t)i * pc + c0)) : make_float4(0.f, 0.f, 0.f, 0.f));
         if (i < 1 || i > h - 2) ringmask |= 1u << r;
     }
-    float2 M[4];                        // 0.25 inside, 0 on the ring columns / outside
+    FzElem M[4];                        // 0.25 inside, 0 on the ring columns / outside
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const float m = (c0 + c >= 1 && c0 + c <= w - 2) ? 0.25f : 0.f;
-        M[c] = make_float2(m, m);
+        M[c] = pe_make<FzElem>(make_float2(m, m));
     }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
@@ -378,7 +385,7 @@ k_step_fused(const FusedArgs a)
 
         FZ_TICK(1);
         // ---- a5 divergence into registers: (((u[i+1][j] - u[i][j]) + v[i][j+1]) - v[i][j]) / dt           :136
-        PackedStrip ND;                 // minus the divergence (x - div == x + (-div))
+        FzStrip ND = {};                // minus the divergence (x - div == x + (-div))
         {
             float4 ua = zlds4(su + r0 * FZ_PU + c0);
 #pragma unroll
@@ -412,7 +419,7 @@ k_step_fused(const FusedArgs a)
         halo[0][1][warp][lane] = packed_row(P, 7);
         __syncthreads();
         {
-            PackedStrip Q;
+            FzStrip Q;
             int s = 0;
             for (; s + 1 < a.K; s += 2) {
                 {
