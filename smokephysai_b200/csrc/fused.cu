@@ -18,7 +18,9 @@
 // the new values of its cells, the CTA synchronises, then everyone writes back.  u's staggered row 128 and v's
 // staggered column 128 (present when h == 128 / w == 128) are spread over lanes 0..7 of every warp.
 // Arithmetic is the same rounded-once sequence as the tiled kernels, so results are bit-identical to them.
+#include <algorithm>
 #include <cstdlib>
+#include <vector>
 #include "common.cuh"
 #include "jacobi_core.cuh"
 
@@ -59,8 +61,8 @@ struct FusedArgs {
     long long su_, sv_, sc_, frame_step_stride, frame_batch_stride;
     float dt, c_uv, c_d, decay;
     int K, nsteps;
-    int nsims, seg_len;                                   // seg_len > 0: time-sliced schedule, see k_step_fused
-    unsigned* progress;                                   // [nsims] steps completed (time-sliced schedule only, zeroed before the launch)
+    const int4* items;                                    // time-sliced schedule (see k_step_fused): (simulation, first step, end step, 0) per CTA, else NULL
+    unsigned* progress;                                   // [nsims] steps completed, zeroed before the launch (time-sliced schedule only)
 #ifdef SMK_FUSED_TIMING
     long long* ticks;
 #endif
@@ -242,15 +244,22 @@ k_step_fused(const FusedArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = FULL ? 128 : a.h, w = FULL ? 128 : a.w;
     const int pu = FULL ? 128 : a.pu, pv = FULL ? 132 : a.pv, pc = FULL ? 128 : a.pc;
-    // Work items.  Classic schedule (seg_len == 0): CTA b runs all nsteps of simulation b.  Time-sliced schedule: the
-    // nsims x nsteps simulation-steps are laid on a line (simulation-major), cut into pieces of seg_len steps, one piece
-    // per CTA; a CTA walks its piece from the END, so a simulation cut by a piece boundary is started (steps 0..) by the
-    // lower CTA as its FIRST item and finished by the next CTA as its LAST item, after the first has published the state
-    // (progress[b], release / acquire at GPU scope).  Waits only ever point at the first item of the previous CTA, which
-    // waits for nothing: no deadlock even if CTAs are not co-resident.  256 simulations x 20 steps on 148 SMs take 35
-    // step-times instead of 40 that way.
-    const int piece_lo = a.seg_len > 0 ? (int)blockIdx.x * a.seg_len : (int)blockIdx.x * a.nsteps;
-    int item_hi = a.seg_len > 0 ? min(piece_lo + a.seg_len, a.nsims * a.nsteps) : piece_lo + a.nsteps;
+    // Work item of this CTA.  Classic schedule (items == NULL): CTA b runs all nsteps of simulation b.  Time-sliced schedule:
+    // the nsims x nsteps simulation-steps are laid on a line (simulation-major) and cut into equal pieces, one piece per SM
+    // (McNaughton's wrap-around rule); a piece is walked from its END, so a simulation cut by a piece boundary is started
+    // (steps 0..) as the FIRST item of the lower piece and finished as the LAST item of the next piece, after the first has
+    // published the state (progress[b], release / acquire at GPU scope).  Every item is a CTA of its own; the host orders
+    // them by planned start time, and because CTAs are dispatched in index order to SMs as they free up, the execution
+    // follows the plan: an item that waits always waits for a CTA of lower index, which is running or done (no deadlock).
+    // 256 simulations x 20 steps on 148 SMs take 35 step-times instead of 40 that way.
+    int4 item = make_int4((int)blockIdx.x, 0, a.nsteps, 0);
+    if (a.items) item = __ldg(a.items + blockIdx.x);
+    const size_t b = (size_t)item.x;
+    const int t_begin = item.y, t_end = item.z;
+    float* __restrict__ gU = a.U + b * a.su_;
+    float* __restrict__ gV = a.V + b * a.sv_;
+    float* __restrict__ gD = a.D + b * a.sc_;
+    float* __restrict__ gP = a.P + b * a.sc_;
     const int r0 = warp * FZ_R, c0 = lane * 4;
     // the staggered extras: u[128][xe] and v[xe][128], xe = 8*warp + lane for lanes 0..7
     const int xe = 8 * warp + lane;
@@ -261,15 +270,7 @@ k_step_fused(const FusedArgs a)
     long long tick0_ = clock64();
 #endif
 
-  while (item_hi > piece_lo) {
-    const size_t b = (size_t)((item_hi - 1) / a.nsteps);
-    const int item_lo = max(piece_lo, (int)b * a.nsteps);
-    const int t_begin = item_lo - (int)b * a.nsteps, t_end = item_hi - (int)b * a.nsteps;
-    float* __restrict__ gU = a.U + b * a.su_;
-    float* __restrict__ gV = a.V + b * a.sv_;
-    float* __restrict__ gD = a.D + b * a.sc_;
-    float* __restrict__ gP = a.P + b * a.sc_;
-    if (t_begin > 0) {                  // the first steps of this simulation ran on the previous CTA: wait for its state
+    if (t_begin > 0) {                  // the first steps of this simulation ran in another CTA: wait for its state
         if (tid == 0) {
             unsigned done;
             do {
@@ -577,13 +578,13 @@ k_step_fused(const FusedArgs a)
             *reinterpret_cast<float4*>(gD + (size_t)i * pc + 4 * g) = zlds4(sd + i * FZ_PD + 4 * g);
         }
     }
-    __syncthreads();                    // shared memory is reloaded by the next item; every thread's stores precede the release
-    if (t_end < a.nsteps && tid == 0) {
-        __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.progress + b), "r"((unsigned)t_end) : "memory");
+    if (t_end < a.nsteps) {             // the rest of this simulation runs in another CTA: publish the state
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.progress + b), "r"((unsigned)t_end) : "memory");
+        }
     }
-    item_hi = item_lo;
-  }
     FZ_TICK(7);
 }
 
@@ -607,12 +608,12 @@ bool fused_supported(const smk_grid_t* g)
            (g->gh == 0 || (g->gh == g->h && g->row0 == 0)) && device_has_room();
 }
 
-// Time-sliced schedule (see k_step_fused): steps per CTA, or 0 for one CTA per simulation.  It pays when the simulations do
+// Time-sliced schedule (see k_step_fused): steps per piece, or 0 for one CTA per simulation.  It pays when the simulations do
 // not fill a whole number of CTA waves: ceil(total / SMs) step-times (+ about one for the extra state hand-overs) against
-// ceil(nsims / SMs) x nsteps.  SMK_FUSED_SLICE = 0 disables it, a positive value forces that many steps per CTA (tests).
+// ceil(nsims / SMs) x nsteps.  SMK_FUSED_SLICE = 0 disables it, a positive value forces that many steps per piece (tests).
 static int pick_seg_len(const smk_grid_t* g, int nsteps, const void* scratch)
 {
-    if (!scratch || !aligned16(scratch) || (int64_t)g->batch > (int64_t)g->h * g->pitch_c) return 0;
+    if (!scratch || !aligned16(scratch)) return 0;
     const int64_t total = (int64_t)g->batch * nsteps;
     if (total > 0x3fffffff) return 0;
     if (const char* e = getenv("SMK_FUSED_SLICE")) {
@@ -625,6 +626,29 @@ static int pick_seg_len(const smk_grid_t* g, int nsteps, const void* scratch)
     const int64_t L = (total + nsm - 1) / nsm;
     const int64_t classic = (int64_t)((g->batch + nsm - 1) / nsm) * nsteps;
     return (L + 1 < classic) ? (int)L : 0;
+}
+
+// The items of the time-sliced schedule in planned start order: pieces of L steps of the simulation-major line, each walked
+// from its end.  An item that does not begin at step 0 is preceded (lower index) by the item that holds the steps before it:
+// that one starts earlier in a piece of lower index, or -- a simulation spanning three or more pieces -- is a whole piece.
+struct FzPlanned { int4 item; int64_t start; int piece; };
+static void plan_items(int nsims, int nsteps, int L, std::vector<int4>& out)
+{
+    const int64_t total = (int64_t)nsims * nsteps;
+    std::vector<FzPlanned> v;
+    for (int64_t lo = 0, c = 0; lo < total; lo += L, ++c) {
+        int64_t x = std::min<int64_t>(lo + L, total), start = 0;
+        while (x > lo) {
+            const int64_t b = (x - 1) / nsteps, ilo = std::max<int64_t>(lo, b * nsteps);
+            v.push_back({make_int4((int)b, (int)(ilo - b * nsteps), (int)(x - b * nsteps), 0), start, (int)c});
+            start += x - ilo;
+            x = ilo;
+        }
+    }
+    // planned start time first; among equal start times the lower piece first (the item a later piece waits for)
+    std::stable_sort(v.begin(), v.end(), [](const FzPlanned& p, const FzPlanned& q) { return p.start != q.start ? p.start < q.start : p.piece < q.piece; });
+    out.resize(v.size());
+    for (size_t k = 0; k < v.size(); ++k) out[k] = v[k].item;
 }
 
 int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float* p, int nsteps, float* frames,
@@ -650,13 +674,30 @@ int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float*
     a.su_ = g->stride_u; a.sv_ = g->stride_v; a.sc_ = g->stride_c;
     a.frame_step_stride = frame_step_stride; a.frame_batch_stride = frame_batch_stride;
     a.dt = dt; a.c_uv = c_uv; a.c_d = c_d; a.decay = decay; a.K = K; a.nsteps = nsteps;
-    a.nsims = g->batch; a.seg_len = pick_seg_len(g, nsteps, scratch); a.progress = reinterpret_cast<unsigned*>(scratch);
+    a.items = nullptr; a.progress = nullptr;
     int ctas = g->batch;
-    if (a.seg_len > 0) {
-        // `scratch` (the divergence array, unused by this kernel) holds the per-simulation progress counters
-        const cudaError_t e = cudaMemsetAsync(a.progress, 0, sizeof(unsigned) * (size_t)g->batch, s);
-        if (e != cudaSuccess) return fail((int)e, "k_step_fused: cudaMemsetAsync of the progress counters: %s", cudaGetErrorString(e));
-        ctas = (int)(((int64_t)g->batch * nsteps + a.seg_len - 1) / a.seg_len);
+    const int seg_len = pick_seg_len(g, nsteps, scratch);
+    if (seg_len > 0) {
+        // `scratch` (the divergence array, which this kernel does not use) holds the per-simulation progress counters
+        // and, behind them, the item table; the plan depends on (simulations, steps, piece length) only and is cached
+        static thread_local std::vector<int4> plan;
+        static thread_local int plan_key[3] = {0, 0, 0};
+        if (plan_key[0] != g->batch || plan_key[1] != nsteps || plan_key[2] != seg_len) {
+            plan_items(g->batch, nsteps, seg_len, plan);
+            plan_key[0] = g->batch; plan_key[1] = nsteps; plan_key[2] = seg_len;
+        }
+        const size_t counters = (sizeof(unsigned) * (size_t)g->batch + 15) & ~(size_t)15;
+        const size_t need = counters + sizeof(int4) * plan.size();
+        const size_t have = sizeof(float) * (size_t)g->stride_c * (size_t)(g->batch - 1) + sizeof(float) * (size_t)g->h * (size_t)g->pitch_c;
+        if (need <= have) {
+            a.progress = reinterpret_cast<unsigned*>(scratch);
+            a.items = reinterpret_cast<const int4*>(reinterpret_cast<char*>(scratch) + counters);
+            cudaError_t e = cudaMemsetAsync(a.progress, 0, counters, s);
+            // pageable source: the runtime stages the table before it returns, the cached vector may change afterwards
+            if (e == cudaSuccess) e = cudaMemcpyAsync(const_cast<int4*>(a.items), plan.data(), sizeof(int4) * plan.size(), cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return fail((int)e, "k_step_fused: upload of the time-sliced schedule: %s", cudaGetErrorString(e));
+            ctas = (int)plan.size();
+        }
     }
     ProfScope prof_(SMK_PH_STEP_FUSED, s);
     if (full) k_step_fused<true><<<ctas, FZ_THREADS, FZ_SMEM, s>>>(a);
