@@ -611,9 +611,12 @@ bool fused_supported(const smk_grid_t* g)
 // Time-sliced schedule (see k_step_fused): steps per piece, or 0 for one CTA per simulation.  It pays when the simulations do
 // not fill a whole number of CTA waves: ceil(total / SMs) step-times (+ about one for the extra state hand-overs) against
 // ceil(nsims / SMs) x nsteps.  SMK_FUSED_SLICE = 0 disables it, a positive value forces that many steps per piece (tests).
-static int pick_seg_len(const smk_grid_t* g, int nsteps, const void* scratch)
+static int pick_seg_len(const smk_grid_t* g, int nsteps, const void* scratch, cudaStream_t s)
 {
     if (!scratch || !aligned16(scratch)) return 0;
+    // the schedule is uploaded from pageable host memory, which a stream capture does not allow
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return 0;
     const int64_t total = (int64_t)g->batch * nsteps;
     if (total > 0x3fffffff) return 0;
     if (const char* e = getenv("SMK_FUSED_SLICE")) {
@@ -676,7 +679,7 @@ int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float*
     a.dt = dt; a.c_uv = c_uv; a.c_d = c_d; a.decay = decay; a.K = K; a.nsteps = nsteps;
     a.items = nullptr; a.progress = nullptr;
     int ctas = g->batch;
-    const int seg_len = pick_seg_len(g, nsteps, scratch);
+    const int seg_len = pick_seg_len(g, nsteps, scratch, s);
     if (seg_len > 0) {
         // `scratch` (the divergence array, which this kernel does not use) holds the per-simulation progress counters
         // and, behind them, the item table; the plan depends on (simulations, steps, piece length) only and is cached
