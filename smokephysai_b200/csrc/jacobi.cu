@@ -438,6 +438,7 @@ static int stream_env()
     return -1;
 }
 
+constexpr int SMK_ENOTMA = -1000;          // internal: no tensor map could be built, the caller falls back to k_jacobi_packed
 // cuTensorMapEncodeTiled through the runtime's driver entry point (nothing of libcuda is linked)
 typedef CUresult (*js_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -456,15 +457,15 @@ static js_encode_fn js_encoder()
 static int js_make_map(CUtensorMap* m, const smk_grid_t* g, const float* base, const int box_rows)
 {
     js_encode_fn enc = js_encoder();
-    if (!enc) return fail(SMK_EUNSUPPORTED, "k_jacobi_stream: cuTensorMapEncodeTiled is not available from this driver");
+    if (!enc) return SMK_ENOTMA;
     const cuuint64_t dims[3] = {(cuuint64_t)g->pitch_c, (cuuint64_t)g->h, (cuuint64_t)g->batch};
-    const cuuint64_t strides[2] = {(cuuint64_t)g->pitch_c * 4u, (cuuint64_t)g->stride_c * 4u};
+    // the stride of the batch dimension is not used when there is one simulation, but it has to be a valid one
+    const cuuint64_t strides[2] = {(cuuint64_t)g->pitch_c * 4u, (g->batch > 1 ? (cuuint64_t)g->stride_c : (cuuint64_t)g->pitch_c * (cuuint64_t)g->h) * 4u};
     const cuuint32_t box[3] = {128, (cuuint32_t)box_rows, 1}, estr[3] = {1, 1, 1};
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(SMK_EINVAL, "k_jacobi_stream: cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d grid", (int)r, g->batch, g->h, g->pitch_c);
-    return SMK_OK;
+    return r == CUDA_SUCCESS ? SMK_OK : SMK_ENOTMA;
 }
 
 template <int NW>
@@ -519,9 +520,11 @@ static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, in
         if (stream_mode == 2 && (g->pitch_c < 128 || g->h < TH)) stream_mode = 1;       // the TMA box is 128 x TH: keep it inside the tensor
         if (stream_mode) {
             rc = launch_stream<(R == 8 && NW == 8) ? 8 : 16>(g, src, dst, div, t, HX, nx, ny, stream_mode, s);
-            if (rc != SMK_OK) return rc;
-            float* tmp = src; src = dst; dst = tmp;
-            continue;
+            if (rc == SMK_OK) {
+                float* tmp = src; src = dst; dst = tmp;
+                continue;
+            }
+            if (rc != SMK_ENOTMA) return rc;             // no tensor map for this grid: the non-streaming kernel below gives the same result
         }
         {
             ProfScope prof_(SMK_PH_JACOBI, s);
