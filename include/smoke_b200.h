@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMK_ABI_VERSION 4
+#define SMK_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define SMK_API __attribute__((visibility("default")))
@@ -178,6 +178,12 @@ SMK_API int smk_run_steps(const smk_grid_t* g, smk_state_t* st, const smk_params
                   const float* fmul, void* stream);
 /*     1 when a call of nsteps steps (smk_step: 1) would take the fused single-launch path for this grid and params */
 SMK_API int smk_step_is_fused(const smk_grid_t* g, const smk_params_t* prm, int32_t nsteps, int32_t* fused_host);
+/* Host-only (no GPU needed): the time-sliced schedule smk_run_steps gives the fused kernel when `nsims` simulations of
+ *     `nsteps` steps do not fill whole waves of SMs.  The nsims x nsteps simulation-steps, simulation-major, are cut into
+ *     pieces of piece_len steps; every item {simulation, first step, end step, 0} is one CTA, listed in launch order.  An
+ *     item with first step > 0 waits for the item of lower index that ends at that step.  items_host holds 4 int32 per
+ *     item, `capacity` items; *count_host receives the number of items (SMK_EINVAL if capacity is too small). */
+SMK_API int smk_fused_plan(int32_t nsims, int32_t nsteps, int32_t piece_len, int32_t* items_host, int32_t capacity, int32_t* count_host);
 
 /* diagnostics: per simulation {max|div|, sum div^2} of the un-normalised divergence of (u, v);
  *     out[2*batch] must be zeroed by the caller; warp-shuffle + atomic reduction. */

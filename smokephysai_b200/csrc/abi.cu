@@ -279,6 +279,17 @@ int smk_step_is_fused(const smk_grid_t* g, const smk_params_t* prm, int32_t nste
     return SMK_OK;
 }
 
+int smk_fused_plan(int32_t nsims, int32_t nsteps, int32_t piece_len, int32_t* items_host, int32_t capacity, int32_t* count_host)
+{
+    if (!count_host || (capacity > 0 && !items_host)) return fail(SMK_EINVAL, "smk_fused_plan: NULL");
+    if (nsims <= 0 || nsteps <= 0 || piece_len <= 0 || capacity < 0 || (int64_t)nsims * nsteps > 0x3fffffff)
+        return fail(SMK_EINVAL, "smk_fused_plan: nsims %d, nsteps %d, piece_len %d", nsims, nsteps, piece_len);
+    int n = 0;
+    const int rc = fused_plan(nsims, nsteps, piece_len, items_host, capacity, &n);
+    *count_host = n;
+    return rc;
+}
+
 int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, float* frame, int64_t frame_stride,
              const float* fmul, void* stream)
 {

@@ -91,6 +91,7 @@ bool fused_supported(const smk_grid_t* g);
 int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float* p, int nsteps, float* frames,
                        int64_t frame_step_stride, int64_t frame_batch_stride, const float* fmul,
                        float dt, float c_uv, float c_d, float decay, int K, float* scratch, cudaStream_t s);
+int fused_plan(int nsims, int nsteps, int piece_len, int32_t* items, int capacity, int* count);
 int launch_apply_mul(const float* f, const float* mul, float* out, int rows, int cols, int pitch, int batch, int64_t stride, cudaStream_t s);
 
 }  // namespace smk

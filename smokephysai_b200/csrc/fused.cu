@@ -654,6 +654,18 @@ static void plan_items(int nsims, int nsteps, int L, std::vector<int4>& out)
     for (size_t k = 0; k < v.size(); ++k) out[k] = v[k].item;
 }
 
+int fused_plan(int nsims, int nsteps, int piece_len, int32_t* items, int capacity, int* count)
+{
+    std::vector<int4> plan;
+    plan_items(nsims, nsteps, piece_len, plan);
+    *count = (int)plan.size();
+    if ((int)plan.size() > capacity) return fail(SMK_EINVAL, "smk_fused_plan: %zu items, capacity %d", plan.size(), capacity);
+    for (size_t k = 0; k < plan.size(); ++k) {
+        items[4 * k] = plan[k].x; items[4 * k + 1] = plan[k].y; items[4 * k + 2] = plan[k].z; items[4 * k + 3] = plan[k].w;
+    }
+    return SMK_OK;
+}
+
 int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float* p, int nsteps, float* frames,
                        int64_t frame_step_stride, int64_t frame_batch_stride, const float* fmul,
                        float dt, float c_uv, float c_d, float decay, int K, float* scratch, cudaStream_t s)

@@ -46,7 +46,7 @@ def test_ctypes_table_matches_header(so_path):
     for name, args in table.items():
         assert len(args) == decl[name], "%s: %d ctypes args vs %d in the header" % (name, len(args), decl[name])
     lib = _lib.load()
-    assert lib.smk_version() == 4
+    assert lib.smk_version() == 5
     assert isinstance(lib.smk_last_error_string(), bytes)
 
 
@@ -117,3 +117,47 @@ def test_no_packed_fma_in_the_library():
     sass = subprocess.run([tool, "-sass", _lib.SO_PATH], capture_output=True, text=True, check=True).stdout
     assert "FADD2" in sass and "FMUL2" in sass, "expected the f32x2 kernels in the library"
     assert "FFMA2" not in sass, "a packed multiply-add was contracted into FFMA2: results would not be rounded-once"
+
+
+@pytest.mark.parametrize("nsims,nsteps,piece", [(256, 20, 35), (5, 7, 3), (5, 7, 9), (4, 6, 1), (7, 4, 28), (300, 1, 3), (149, 100, 101), (1, 50, 7)])
+def test_fused_time_sliced_plan(so_path, nsims, nsteps, piece):
+    """smk_fused_plan (host only): the items cover every simulation-step once, an item that continues a simulation comes after
+    the item that ends where it begins, and a machine that hands the items out in index order to `sms` workers as they free
+    up -- what the GPU's CTA dispatch does -- finishes within the piece length plus the waits the plan itself contains."""
+    import ctypes as C
+    from smokephysai_b200 import _lib
+    lib = _lib.load()
+    cap = nsims * nsteps
+    buf = (C.c_int32 * (4 * cap))()
+    n = C.c_int32(0)
+    assert lib.smk_fused_plan(nsims, nsteps, piece, buf, cap, C.byref(n)) == 0
+    items = [tuple(buf[4 * k: 4 * k + 3]) for k in range(n.value)]
+    seen = set()
+    ends = {}
+    for k, (b, t0, t1) in enumerate(items):
+        assert 0 <= b < nsims and 0 <= t0 < t1 <= nsteps and t1 - t0 <= piece
+        if t0 > 0:
+            assert (b, t0) in ends and ends[(b, t0)] < k, "item %d continues a simulation nobody has advanced to step %d" % (k, t0)
+        ends[(b, t1)] = k
+        for t in range(t0, t1):
+            assert (b, t) not in seen
+            seen.add((b, t))
+    assert len(seen) == nsims * nsteps
+    npieces = -(-nsims * nsteps // piece)
+    assert n.value <= nsims + npieces
+    # in-order dispatch onto as many workers as there are pieces: event simulation in units of one step
+    import heapq
+    free = [(0, w) for w in range(npieces)]
+    heapq.heapify(free)
+    done_at = {}
+    makespan = 0
+    for b, t0, t1 in items:
+        t_free, w = heapq.heappop(free)
+        start = max(t_free, done_at.get((b, t0), 0))
+        end = start + (t1 - t0)
+        done_at[(b, t1)] = end
+        makespan = max(makespan, end)
+        heapq.heappush(free, (end, w))
+    assert makespan <= max(piece, nsteps), "makespan %d steps for pieces of %d" % (makespan, piece)
+    # too small a buffer is an error, not an overrun
+    assert lib.smk_fused_plan(nsims, nsteps, piece, buf, 0, C.byref(n)) != 0 and n.value == len(items)
