@@ -235,6 +235,9 @@ __device__ __forceinline__ void js_stage(const JsArgs& a, const CUtensorMap* mp,
     const int x0 = c.bx * a.ox, y0 = c.by * a.oy;
     if (TMA) {
         if (threadIdx.x == 0) {
+            // the strip reads of the previous tile (generic proxy, ordered before this point by the CTA barrier) precede the
+            // TMA writes (async proxy) into the same buffer
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                          :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(2u * (unsigned)TH * 128u * 4u) : "memory");
             js_tma_tile(&sp[0][0], mp, x0, y0, c.bz, bar);
