@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <vector>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace smk {
@@ -18,6 +19,16 @@ int fail(int code, const char* fmt, ...)
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
+}
+
+// SMK_PDL=0 switches programmatic dependent launch off; never inside a stream capture (plain kernel nodes there)
+bool pdl_enabled(cudaStream_t s)
+{
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("SMK_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }
+    if (!on) return false;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
 }
 
 int check_launch(const char* what)

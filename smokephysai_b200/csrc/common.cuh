@@ -56,6 +56,32 @@ struct GlobalField {
     __device__ __forceinline__ float operator()(int i, int j) const { return __ldg(p + (size_t)i * pitch + j); }
 };
 
+// ---- programmatic dependent launch -------------------------------------------------------------------------
+// The phase-per-kernel path is a chain of dependent kernels on one stream (10 per step at 1024^2, K = 100), each a few
+// microseconds long: the gap between "last CTA of kernel n exits" and "first CTA of kernel n + 1 runs" is paid ten
+// times per step.  Kernels of the chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization and start with
+// pdl_prologue(): griddepcontrol.wait blocks until the previous kernel has completed and its writes are visible (so every
+// global access of the kernel stays ordered after it), griddepcontrol.launch_dependents lets the NEXT kernel's CTAs
+// be scheduled as soon as this kernel's CTAs have all started, so its launch latency and prologue overlap this kernel.
+// SMK_PDL=0 launches the chain the classic way.  A kernel launched without the attribute runs pdl_prologue() as no-ops.
+__device__ __forceinline__ void pdl_prologue()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled(cudaStream_t s);
+template <class... P, class... A>
+inline void launch_chain(void (*kernel)(P...), const dim3 grid, const dim3 block, const size_t smem, cudaStream_t s, A&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr = {};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = pdl_enabled(s) ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, P(args)...);          // errors are picked up by check_launch()
+}
+
 // thread-local error string + checks (abi.cu)
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);

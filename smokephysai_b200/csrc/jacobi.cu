@@ -31,6 +31,7 @@ k_jacobi(const float* __restrict__ pin, float* __restrict__ pout, const float* _
          const int h, const int w, const int pitch, const long long bstride,
          const int T, const int HX, const int ox, const int oy)
 {
+    pdl_prologue();
     __shared__ float4 halo[2][2][NW][32];          // [buffer][0: first row, 1: last row][warp][lane]
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -97,6 +98,7 @@ k_jacobi_packed(const float* __restrict__ pin, float* __restrict__ pout, const f
                 const int h, const int w, const int pitch, const long long bstride,
                 const int T, const int HX, const int ox, const int oy)
 {
+    pdl_prologue();
     static_assert(R == 8, "the packed strip pairs row r with row r + 4");
     __shared__ float4 halo[2][2][NW][32];
 
@@ -350,6 +352,7 @@ template <int PMASK, bool TMA, int NW>
 __global__ void __launch_bounds__(NW * 32, (NW * 32 <= 256) ? 2 : 1)
 k_jacobi_stream(const __grid_constant__ JsArgs ga, const __grid_constant__ CUtensorMap mp, const __grid_constant__ CUtensorMap md)
 {
+    pdl_prologue();
     extern __shared__ __align__(128) float js_smem[];
     static_assert(sizeof(JsArgs) <= 96, "js_smem_bytes reserves 96 bytes for the argument copy");
     // js_tile is a separate function: it reads the arguments from shared memory (generic loads of the kernel parameters
@@ -499,8 +502,8 @@ static int launch_stream(const smk_grid_t* g, const float* src, float* dst, cons
         if (rc != SMK_OK) return rc;
     }
     ProfScope prof_(SMK_PH_JACOBI, s);
-    if (mode == 1) k_jacobi_stream<6, false, NW><<<ctas, NW * 32, SMEM, s>>>(a, mp, md);
-    else           k_jacobi_stream<6, true, NW><<<ctas, NW * 32, SMEM, s>>>(a, mp, md);
+    if (mode == 1) launch_chain(k_jacobi_stream<6, false, NW>, dim3(ctas), dim3(NW * 32), SMEM, s, a, mp, md);
+    else           launch_chain(k_jacobi_stream<6, true, NW>, dim3(ctas), dim3(NW * 32), SMEM, s, a, mp, md);
     return check_launch("k_jacobi_stream");
 }
 
@@ -531,16 +534,16 @@ static int run_cfg(const smk_grid_t* g, const float* div, float* a, float* b, in
         }
         {
             ProfScope prof_(SMK_PH_JACOBI, s);
-#define SMK_PACKED_CASE(M) case M: k_jacobi_packed<8, NW, M><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c, \
+#define SMK_PACKED_CASE(M) case M: launch_chain(k_jacobi_packed<8, NW, M>, grid, dim3(NW * 32), 0, s, src, dst, div, g->h, g->w, g->pitch_c, \
                                                            (long long)g->stride_c, t, HX, 128 - 2 * HX, TH - 2 * t); break;
             if (R == 8 && use_packed()) {
                 switch (use_packed()) {
                     SMK_PACKED_CASE(6) SMK_PACKED_CASE(9) SMK_PACKED_CASE(2) SMK_PACKED_CASE(7) SMK_PACKED_CASE(16)
-                    default: k_jacobi_packed<8, NW, 15><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c,
+                    default: launch_chain(k_jacobi_packed<8, NW, 15>, grid, dim3(NW * 32), 0, s, src, dst, div, g->h, g->w, g->pitch_c,
                                                            (long long)g->stride_c, t, HX, 128 - 2 * HX, TH - 2 * t);
                 }
             } else
-                k_jacobi<R, NW><<<grid, NW * 32, 0, s>>>(src, dst, div, g->h, g->w, g->pitch_c, (long long)g->stride_c,
+                launch_chain(k_jacobi<R, NW>, grid, dim3(NW * 32), 0, s, src, dst, div, g->h, g->w, g->pitch_c, (long long)g->stride_c,
                                                          t, HX, 128 - 2 * HX, TH - 2 * t);
             rc = check_launch("k_jacobi");
         }

@@ -206,6 +206,7 @@ k_forces_diffuse_div(const float* __restrict__ U, const float* __restrict__ V, c
                      const long long su_, const long long sv_, const long long sc_,
                      const float dt, const float c_uv, const float c_d, const int bulk)
 {
+    pdl_prologue();
     __shared__ __align__(16) FddTile T;
     const int i0 = blockIdx.y * FTH, j0 = blockIdx.x * FTW;
     const size_t b = blockIdx.z;
@@ -227,7 +228,7 @@ int launch_forces_diffuse_div(const smk_grid_t* g, const float* u, const float* 
     ProfScope prof_(SMK_PH_FORCES_DIFFUSE_DIV, s);
     int bulk = (int64_t)g->h * g->w * g->batch >= ((int64_t)6 << 20) ? 1 : 0;
     if (const char* e = getenv("SMK_FDD_BULK")) bulk = atoi(e) != 0;       // tests force either staging path on small grids
-    k_forces_diffuse_div<<<grid, FTHREADS, 0, s>>>(u, v, d, uo, vo, dout, div, g->h, g->w, g->pitch_u, g->pitch_v, g->pitch_c,
+    launch_chain(k_forces_diffuse_div, grid, dim3(FTHREADS), 0, s, u, v, d, uo, vo, dout, div, g->h, g->w, g->pitch_u, g->pitch_v, g->pitch_c,
                                                    g->stride_u, g->stride_v, g->stride_c, dt, c_uv, c_d, bulk);
     return check_launch("k_forces_diffuse_div");
 }
@@ -287,6 +288,7 @@ k_project(const float* __restrict__ P, float* __restrict__ U, float* __restrict_
           const int h, const int w, const int pu, const int pv, const int pc,
           const long long su_, const long long sv_, const long long sc_, const float dt)
 {
+    pdl_prologue();
     const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4, i = blockIdx.y * 8 + threadIdx.y;
     const size_t b = blockIdx.z;
     P += b * sc_; U += b * su_; V += b * sv_;
@@ -337,7 +339,7 @@ int launch_project(const smk_grid_t* g, const float* p, float* u, float* v, floa
 {
     dim3 grid((g->w + 127) / 128, (g->h + 7) / 8, g->batch), blk(32, 8);
     ProfScope prof_(SMK_PH_PROJECT, s);
-    k_project<<<grid, blk, 0, s>>>(p, u, v, g->h, g->w, g->pitch_u, g->pitch_v, g->pitch_c,
+    launch_chain(k_project, grid, blk, 0, s, p, u, v, g->h, g->w, g->pitch_u, g->pitch_v, g->pitch_c,
                                    g->stride_u, g->stride_v, g->stride_c, dt);
     return check_launch("k_project");
 }
@@ -384,6 +386,7 @@ template <bool SLAB>
 __global__ void __launch_bounds__(256)
 k_advect(const AdvectArgs a)
 {
+    pdl_prologue();
     const unsigned idx = blockIdx.x * 256u + threadIdx.x;
     unsigned row = (unsigned)(((unsigned long long)idx * a.magic) >> 40);
     if (row * a.ngroups > idx) --row;
@@ -662,6 +665,7 @@ template <bool SLAB>
 __global__ void __launch_bounds__(256, 6)        // 40 registers: 6 CTAs per SM beat 4 (62 registers) by 12 % and 7 (32, spills) by 5 %
 k_advect_tiled(const AdvectArgs a)
 {
+    pdl_prologue();
     __shared__ __align__(16) AdvectTile T;
     const int i0 = blockIdx.y * AT_R, j0 = blockIdx.x * AT_C;
     const size_t b = blockIdx.z;
@@ -710,12 +714,12 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
     const bool big = (int64_t)rows * cols * g->batch >= (int64_t)6 << 20;
     if ((tiled == 1 || (tiled == -1 && big)) && (rows + AT_R - 1) / AT_R <= 65535) {
         dim3 tgrid((unsigned)((pitch + AT_C - 1) / AT_C), (unsigned)((rows + AT_R - 1) / AT_R), g->batch);
-        if (slab) k_advect_tiled<true><<<tgrid, 256, 0, s>>>(a);
-        else      k_advect_tiled<false><<<tgrid, 256, 0, s>>>(a);
+        if (slab) launch_chain(k_advect_tiled<true>, tgrid, dim3(256), 0, s, a);
+        else      launch_chain(k_advect_tiled<false>, tgrid, dim3(256), 0, s, a);
         return check_launch("k_advect_tiled");
     }
-    if (slab) k_advect<true><<<grid, 256, 0, s>>>(a);
-    else      k_advect<false><<<grid, 256, 0, s>>>(a);
+    if (slab) launch_chain(k_advect<true>, grid, dim3(256), 0, s, a);
+    else      launch_chain(k_advect<false>, grid, dim3(256), 0, s, a);
     return check_launch("k_advect");
 }
 
