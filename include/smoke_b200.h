@@ -99,9 +99,9 @@ typedef struct smk_params {
  *   SMK_STEP_FUSED   the whole simulation on one SM -- u, v, density in shared memory, pressure in registers --
  *                    for all the steps of the call in a single launch; grids of at most 128 x 128 cells only
  *                    (SMK_EUNSUPPORTED otherwise)
- *   SMK_STEP_AUTO    fused when the grid qualifies and the call carries enough work for one-simulation-per-SM
- *                    execution to win: at least 96 x 96 cells, and two or more steps per call or one step of at
- *                    least 32 simulations                                                                   */
+ *   SMK_STEP_AUTO    fused when the grid qualifies and the call carries enough simulations for one-simulation-per-SM
+ *                    execution to win: 128 x 128 cells and at least 12 simulations (48 for a single-step call), or
+ *                    at least 96 x 96 cells and 96 simulations; the phase kernels otherwise                  */
 enum { SMK_STEP_AUTO = 0, SMK_STEP_PHASES = 1, SMK_STEP_FUSED = 2 };
 
 SMK_API int smk_version(void);

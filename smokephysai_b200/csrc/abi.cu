@@ -269,10 +269,16 @@ static int pick_step_kernel(const smk_grid_t* g, const smk_params_t* prm, int ns
     if (prm->step_kernel != SMK_STEP_AUTO && prm->step_kernel != SMK_STEP_FUSED)
         return fail(SMK_EINVAL, "smk_step: step_kernel %d is not SMK_STEP_AUTO/_PHASES/_FUSED", prm->step_kernel);
     if (fused_supported(g)) {
-        // a CTA costs the same whatever the grid size, so small grids are better off on the phase kernels:
-        // 96 x 96 still wins fused (63 against 77 us per step of 148 simulations), 64 x 64 loses (65 against 52)
+        // One simulation per SM pays when there are enough simulations to fill the SMs; a few simulations are faster on the
+        // phase kernels spread over all SMs, whose launch gaps programmatic dependent launch has removed.  Measured per step
+        // (tools/step_latency_sizes.py, K = 20): 128 x 128: 1 simulation 27.6 us on the phase path against 30.0 fused (20-step
+        // calls), 8 simulations equal, 32 simulations 38.7 against 30.0; single-step calls 39.8 against 45.3 at 32 simulations.
+        // 96 x 96 (generic fused kernel): 32 simulations 36.8 against 47.8, 148 simulations 77 against 63.  Below 96 x 96
+        // the phase path always wins (64 x 64: 52 against 65 us per step of 148 simulations).
+        const bool full = g->h == 128 && g->w == 128;
         const bool big_enough = (long)g->h * g->w >= 96L * 96L;
-        *fused = (prm->step_kernel == SMK_STEP_FUSED || (big_enough && (nsteps >= 2 || g->batch >= 32))) ? 1 : 0;
+        const int need = full ? (nsteps >= 2 ? 12 : 48) : 96;
+        *fused = (prm->step_kernel == SMK_STEP_FUSED || (big_enough && g->batch >= need)) ? 1 : 0;
         return SMK_OK;
     }
     if (prm->step_kernel == SMK_STEP_FUSED)
