@@ -580,45 +580,71 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
             // a8 (:111-131) with x0 = floor(px) already inside [0, cols-1]
             const float2 fx0 = make_float2(floorf(px.x), floorf(px.y)), fy0 = make_float2(floorf(py.x), floorf(py.y));
             float2 fx1 = __fadd2_rn(fx0, one2), fy1 = __fadd2_rn(fy0, one2);
-            fx1.x = fminf(fx1.x, xmax); fx1.y = fminf(fx1.y, xmax);
-            fy1.x = fminf(fy1.x, ymax); fy1.y = fminf(fy1.y, ymax);
-            const float2 ax = __fadd2_rn(fx1, neg2(px)), bx = __fadd2_rn(px, neg2(fx0));
-            const float2 ay = __fadd2_rn(fy1, neg2(py)), by = __fadd2_rn(py, neg2(fy0));
             const int x0a = (int)fx0.x, x0b = (int)fx0.y;
             int y0a = (int)fy0.x, y0b = (int)fy0.y;
-            const int dxa = (fx1.x != fx0.x) ? 1 : 0, dxb = (fx1.y != fx0.y) ? 1 : 0;
-            int dya = (fy1.x != fy0.x) ? 1 : 0, dyb = (fy1.y != fy0.y) ? 1 : 0;
-            if (SLAB) {                                                         // global -> local row, kept inside the slab
-                y0a -= a.row0; y0b -= a.row0;
-                const int y1a = y0a + dya, y1b = y0b + dyb;
-                if (i >= a.need_lo && i < a.need_hi && a.overflow &&
-                    ((j < cols && (y0a < a.valid_lo || y1a >= a.valid_hi)) || (j1 < cols && (y0b < a.valid_lo || y1b >= a.valid_hi))))
-                    *a.overflow = 1;
-                if (y1a > rows - 1) dya = 0;
-                if (y1b > rows - 1) dyb = 0;
-                y0a = clampi(y0a, 0, rows - 1); y0b = clampi(y0b, 0, rows - 1);
-            }
-            // both cells of the pair inside the staged window (with room for the +1 corners)?
-            const int lya = y0a - wy_org, lxa = x0a - wx_org, lyb = y0b - wy_org, lxb = x0b - wx_org;
-            bool inwin;
-            if (INTERIOR) inwin = ((unsigned)lya < (unsigned)(AT_FR - 1)) & ((unsigned)lxa < (unsigned)(AT_FP - 1)) &
-                                  ((unsigned)lyb < (unsigned)(AT_FR - 1)) & ((unsigned)lxb < (unsigned)(AT_FP - 1));
-            else inwin = y0a >= wy0 && y0a + dya < wy1 && x0a >= wx0 && x0a + dxa < wx1 &&
-                         y0b >= wy0 && y0b + dyb < wy1 && x0b >= wx0 && x0b + dxb < wx1;
             float2 f00, f01, f10, f11;
-            if (inwin) {
-                const float* qa = sF0 + (lya * AT_FP + lxa);
-                const float* qb = sF0 + (lyb * AT_FP + lxb);
-                const int oya = dya * AT_FP, oyb = dyb * AT_FP;
-                f00 = make_float2(qa[0], qb[0]); f01 = make_float2(qa[dxa], qb[dxb]);
-                f10 = make_float2(qa[oya], qb[oyb]); f11 = make_float2(qa[oya + dxa], qb[oyb + dxb]);
+            if (INTERIOR && !SLAB) {
+                // The window of an interior tile lies inside the field, so a pair whose lower corners are inside the window
+                // (with room for the +1 corners) has x0 + 1 <= cols - 1 and y0 + 1 <= rows - 1: the clamps of the upper corners
+                // (:121, :123) do not bind and the corner offsets are the constants 1 and AT_FP.  Only the pairs that leave
+                // the window clamp, compare and gather from global memory.
+                const int lya = y0a - wy_org, lxa = x0a - wx_org, lyb = y0b - wy_org, lxb = x0b - wx_org;
+                const bool inwin = ((unsigned)lya < (unsigned)(AT_FR - 1)) & ((unsigned)lxa < (unsigned)(AT_FP - 1)) &
+                                   ((unsigned)lyb < (unsigned)(AT_FR - 1)) & ((unsigned)lxb < (unsigned)(AT_FP - 1));
+                if (inwin) {
+                    const float* qa = sF0 + (lya * AT_FP + lxa);
+                    const float* qb = sF0 + (lyb * AT_FP + lxb);
+                    f00 = make_float2(qa[0], qb[0]); f01 = make_float2(qa[1], qb[1]);
+                    f10 = make_float2(qa[AT_FP], qb[AT_FP]); f11 = make_float2(qa[AT_FP + 1], qb[AT_FP + 1]);
+                } else {
+                    fx1.x = fminf(fx1.x, xmax); fx1.y = fminf(fx1.y, xmax);
+                    fy1.x = fminf(fy1.x, ymax); fy1.y = fminf(fy1.y, ymax);
+                    const int dxa = (fx1.x != fx0.x) ? 1 : 0, dxb = (fx1.y != fx0.y) ? 1 : 0;
+                    const int dya = (fy1.x != fy0.x) ? 1 : 0, dyb = (fy1.y != fy0.y) ? 1 : 0;
+                    const float* qa = F + ((unsigned)y0a * pitch + x0a);
+                    const float* qb = F + ((unsigned)y0b * pitch + x0b);
+                    const int oya = dya * pitch, oyb = dyb * pitch;
+                    f00 = make_float2(__ldg(qa), __ldg(qb)); f01 = make_float2(__ldg(qa + dxa), __ldg(qb + dxb));
+                    f10 = make_float2(__ldg(qa + oya), __ldg(qb + oyb)); f11 = make_float2(__ldg(qa + oya + dxa), __ldg(qb + oyb + dxb));
+                }
             } else {
-                const float* qa = F + ((unsigned)y0a * pitch + x0a);
-                const float* qb = F + ((unsigned)y0b * pitch + x0b);
-                const int oya = dya * pitch, oyb = dyb * pitch;
-                f00 = make_float2(__ldg(qa), __ldg(qb)); f01 = make_float2(__ldg(qa + dxa), __ldg(qb + dxb));
-                f10 = make_float2(__ldg(qa + oya), __ldg(qb + oyb)); f11 = make_float2(__ldg(qa + oya + dxa), __ldg(qb + oyb + dxb));
+                fx1.x = fminf(fx1.x, xmax); fx1.y = fminf(fx1.y, xmax);
+                fy1.x = fminf(fy1.x, ymax); fy1.y = fminf(fy1.y, ymax);
+                const int dxa = (fx1.x != fx0.x) ? 1 : 0, dxb = (fx1.y != fx0.y) ? 1 : 0;
+                int dya = (fy1.x != fy0.x) ? 1 : 0, dyb = (fy1.y != fy0.y) ? 1 : 0;
+                if (SLAB) {                                                         // global -> local row, kept inside the slab
+                    y0a -= a.row0; y0b -= a.row0;
+                    const int y1a = y0a + dya, y1b = y0b + dyb;
+                    if (i >= a.need_lo && i < a.need_hi && a.overflow &&
+                        ((j < cols && (y0a < a.valid_lo || y1a >= a.valid_hi)) || (j1 < cols && (y0b < a.valid_lo || y1b >= a.valid_hi))))
+                        *a.overflow = 1;
+                    if (y1a > rows - 1) dya = 0;
+                    if (y1b > rows - 1) dyb = 0;
+                    y0a = clampi(y0a, 0, rows - 1); y0b = clampi(y0b, 0, rows - 1);
+                }
+                // both cells of the pair inside the staged window (with room for the +1 corners)?
+                const int lya = y0a - wy_org, lxa = x0a - wx_org, lyb = y0b - wy_org, lxb = x0b - wx_org;
+                bool inwin;
+                if (INTERIOR) inwin = ((unsigned)lya < (unsigned)(AT_FR - 1)) & ((unsigned)lxa < (unsigned)(AT_FP - 1)) &
+                                      ((unsigned)lyb < (unsigned)(AT_FR - 1)) & ((unsigned)lxb < (unsigned)(AT_FP - 1));
+                else inwin = y0a >= wy0 && y0a + dya < wy1 && x0a >= wx0 && x0a + dxa < wx1 &&
+                             y0b >= wy0 && y0b + dyb < wy1 && x0b >= wx0 && x0b + dxb < wx1;
+                if (inwin) {
+                    const float* qa = sF0 + (lya * AT_FP + lxa);
+                    const float* qb = sF0 + (lyb * AT_FP + lxb);
+                    const int oya = dya * AT_FP, oyb = dyb * AT_FP;
+                    f00 = make_float2(qa[0], qb[0]); f01 = make_float2(qa[dxa], qb[dxb]);
+                    f10 = make_float2(qa[oya], qb[oyb]); f11 = make_float2(qa[oya + dxa], qb[oyb + dxb]);
+                } else {
+                    const float* qa = F + ((unsigned)y0a * pitch + x0a);
+                    const float* qb = F + ((unsigned)y0b * pitch + x0b);
+                    const int oya = dya * pitch, oyb = dyb * pitch;
+                    f00 = make_float2(__ldg(qa), __ldg(qb)); f01 = make_float2(__ldg(qa + dxa), __ldg(qb + dxb));
+                    f10 = make_float2(__ldg(qa + oya), __ldg(qb + oyb)); f11 = make_float2(__ldg(qa + oya + dxa), __ldg(qb + oyb + dxb));
+                }
             }
+            const float2 ax = __fadd2_rn(fx1, neg2(px)), bx = __fadd2_rn(px, neg2(fx0));
+            const float2 ay = __fadd2_rn(fy1, neg2(py)), by = __fadd2_rn(py, neg2(fy0));
             const float2 t00 = __fmul2_rn(__fmul2_rn(ax, ay), f00), t01 = __fmul2_rn(__fmul2_rn(bx, ay), f01);
             const float2 t10 = __fmul2_rn(__fmul2_rn(ax, by), f10), t11 = __fmul2_rn(__fmul2_rn(bx, by), f11);
             float2 sum = make_float2(t00.x + t01.x, t00.y + t01.y);
