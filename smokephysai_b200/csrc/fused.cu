@@ -18,6 +18,10 @@
 // the new values of its cells, the CTA synchronises, then everyone writes back.  u's staggered row 128 and v's
 // staggered column 128 (present when h == 128 / w == 128) are spread over lanes 0..7 of every warp.
 // Arithmetic is the same rounded-once sequence as the tiled kernels, so results are bit-identical to them.
+//
+// Scheduling: one CTA per simulation, or -- when the simulations do not fill whole waves of SMs -- the time-sliced
+// schedule (plan_items / pick_seg_len below): the simulation-steps of the call are cut into equal pieces per SM, a
+// simulation that straddles a piece boundary is handed from one CTA to another through global memory.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>

@@ -17,6 +17,10 @@
 // per-cell multiplier (0.25 inside, 0 on the ring/outside), which costs no extra instruction.
 //
 // Bit-exactness: the association above is kept literally; 0.25*x == x*0.25 in IEEE; no FMA (-fmad=false).
+//
+// Kernels: k_jacobi (scalar strips), k_jacobi_packed (f32x2 row pairs, the default up to a few CTA waves) and
+// k_jacobi_stream (persistent CTAs that prefetch their next tile with TMA tensor loads, the default from four CTA
+// waves); launch_jacobi at the end of the file picks tile shape, sweeps per launch and kernel.
 #include <cstdlib>
 #include <cstring>
 #include <cuda.h>
