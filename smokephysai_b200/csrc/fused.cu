@@ -276,10 +276,13 @@ k_step_fused(const FusedArgs a)
 
     if (t_begin > 0) {                  // the first steps of this simulation ran in another CTA: wait for its state
         if (tid == 0) {
-            unsigned done;
+            unsigned done, spins = 0;
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(a.progress + b) : "memory");
-                if (done < (unsigned)t_begin) __nanosleep(200);
+                if (done < (unsigned)t_begin) {
+                    __nanosleep(200);
+                    if (++spins > (1u << 25)) __trap();      // > 6 s: the producer CTA never ran -- fail the launch instead of hanging the GPU
+                }
             } while (done < (unsigned)t_begin);
         }
         __syncthreads();
