@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMK_ABI_VERSION 5
+#define SMK_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define SMK_API __attribute__((visibility("default")))
@@ -113,6 +113,11 @@ SMK_API int smk_launch_count(int64_t* count);
 /* make `device` current for this thread inside the library's (statically linked) CUDA runtime */
 SMK_API int smk_set_device(int32_t device);
 
+/* The library reads its tuning / test switches (SMK_PDL, SMK_FUSED_SLICE, SMK_FUSED_CLUSTER, SMK_JACOBI_PACKED,
+ * SMK_JACOBI_STREAM, SMK_JACOBI_TILE, SMK_FDD_BULK, SMK_ADVECT_TILED, SMK_PROJECT_FUSED) from the environment once, at
+ * the first launch that needs one; smk_reload_env reads them again (tests change them between cases). */
+SMK_API int smk_reload_env(void);
+
 /* Per-kernel device timing, for bench.py's roofline line: while a profile is open every kernel the library
  * launches is bracketed by a pair of CUDA events recorded on the launching stream.  smk_profile_end
  * synchronises those events, adds the elapsed milliseconds and launch counts up per phase, and closes the
@@ -188,6 +193,10 @@ SMK_API int smk_fused_plan(int32_t nsims, int32_t nsteps, int32_t piece_len, int
 /* diagnostics: per simulation {max|div|, sum div^2} of the un-normalised divergence of (u, v);
  *     out[2*batch] must be zeroed by the caller; warp-shuffle + atomic reduction. */
 SMK_API int smk_div_norms(const smk_grid_t* g, const float* u, const float* v, float* out, void* stream);
+
+/*     per simulation {max|p' - p|, sum (p' - p)^2} where p' is one more Jacobi sweep (navier_stokes.py:139-145) over
+ *     (p, div): the residual of the pressure iteration after the K sweeps of a step.  out[2*batch] zeroed by the caller. */
+SMK_API int smk_jacobi_residual(const smk_grid_t* g, const float* div, const float* p, float* out, void* stream);
 
 /* a13 FractalGenerator fields (fractal_generator.py:12-62).  Output index [a][b], a < na (= w), b < nb (= h),
  *     as torch.meshgrid(x_w, y_h, indexing='ij') lays them out.  Any of the three outputs may be NULL:

@@ -4,6 +4,7 @@ There is no fallback: if the shared object is missing or a call fails, this rais
 """
 import ctypes as C
 import os
+import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libsmoke_sm100.so")
@@ -53,6 +54,7 @@ SIGNATURES = {
     "smk_device_info": [C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32)],
     "smk_launch_count": [C.POINTER(c_i64)],
     "smk_set_device": [c_i32],
+    "smk_reload_env": [],
     "smk_profile_begin": [c_i32],
     "smk_profile_end": [C.POINTER(C.c_double), C.POINTER(c_i64), c_i32],
     "smk_splat_sources": [GP, c_p, c_p, c_p, c_p],
@@ -69,6 +71,7 @@ SIGNATURES = {
     "smk_step_is_fused": [GP, PP, c_i32, C.POINTER(c_i32)],
     "smk_fused_plan": [c_i32, c_i32, c_i32, C.POINTER(c_i32), c_i32, C.POINTER(c_i32)],
     "smk_div_norms": [GP, c_p, c_p, c_p, c_p],
+    "smk_jacobi_residual": [GP, c_p, c_p, c_p, c_p],
     "smk_fractal_fields": [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f, c_i32, c_p, c_p, c_p, c_p, c_p],
     "smk_frame_features": [c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_f, c_f, c_p, c_p, c_p, c_p],
     "smk_frame_distances": [c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
@@ -115,6 +118,65 @@ def check(rc, what):
 
 def call(name, *args):
     check(getattr(load(), name)(*args), name)
+
+
+_tls = threading.local()
+
+
+def stream_on(device):
+    """torch's current stream on `device` (a torch.device with an index); binds the library's own (statically linked)
+    CUDA runtime to that device the first time this thread launches there.  Callers whose device may differ from the
+    thread's current one wrap the launches in `on_device(device)`."""
+    import torch
+    idx = device.index
+    if getattr(_tls, "bound", None) != idx:
+        call("smk_set_device", idx)
+        _tls.bound = idx
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class on_device:
+    """Scope in which `device` is the thread's current CUDA device, for torch and for the library alike; the previous
+    device is restored on exit, so a simulator built on cuda:1 never changes the process's current device behind the
+    caller's back (both runtimes share the driver's per-thread current context).  Free when `device` already is current."""
+
+    def __init__(self, device):
+        self.idx = device.index
+        self.prev = None
+
+    def __enter__(self):
+        import torch
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+            call("smk_set_device", self.idx)
+            _tls.bound = self.idx
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            import torch
+            call("smk_set_device", self.prev)
+            torch.cuda.set_device(self.prev)
+            _tls.bound = self.prev
+        return False
+
+
+def scoped(fn):
+    """Method decorator: run with self._cuda as the current device (see on_device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with on_device(self._cuda):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
+def reload_env():
+    """Make the library read its SMK_* environment switches again (it reads them once per process otherwise)."""
+    call("smk_reload_env")
 
 
 def launch_count():

@@ -20,8 +20,7 @@ def _edges_for(dev):
 
 
 def _stream(dev):
-    _lib.call("smk_set_device", dev.index)
-    return torch.cuda.current_stream(dev).cuda_stream
+    return _lib.stream_on(dev)
 
 
 def frame_counts(frames, w):
@@ -30,8 +29,9 @@ def frame_counts(frames, w):
     dev = frames.device
     box = torch.empty(n, len(SCALES), dtype=torch.int32, device=dev)
     hist = torch.empty(n, NBINS, dtype=torch.int32, device=dev)
-    _lib.call("smk_frame_features", frames.data_ptr(), h * pitch, n, h, w, pitch, _edges_for(dev).data_ptr(), NBINS, 0.0, 1.0,
-              box.data_ptr(), hist.data_ptr(), None, _stream(dev))
+    with _lib.on_device(dev):
+        _lib.call("smk_frame_features", frames.data_ptr(), h * pitch, n, h, w, pitch, _edges_for(dev).data_ptr(), NBINS, 0.0, 1.0,
+                  box.data_ptr(), hist.data_ptr(), None, _stream(dev))
     return box, hist
 
 
@@ -41,7 +41,8 @@ def frame_distances(frames, w):
     if n < 2:
         return np.zeros(0)
     out = torch.empty(n - 1, dtype=torch.float64, device=frames.device)
-    _lib.call("smk_frame_distances", frames.data_ptr(), h * pitch, n, h, w, pitch, out.data_ptr(), _stream(frames.device))
+    with _lib.on_device(frames.device):
+        _lib.call("smk_frame_distances", frames.data_ptr(), h * pitch, n, h, w, pitch, out.data_ptr(), _stream(frames.device))
     return out.sqrt().float().cpu().numpy().astype(np.float64)
 
 

@@ -1,6 +1,7 @@
 // abi.cu -- the extern "C" surface of libsmoke_sm100.so (include/smoke_b200.h): argument validation,
 // thread-local error string, and the whole-step orchestration of navier_stokes.py:151-173.
 #include <atomic>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <vector>
@@ -21,12 +22,43 @@ int fail(int code, const char* fmt, ...)
     return code;
 }
 
+// ---- environment switches: read once, re-read on smk_reload_env() ------------------------------------------
+static EnvCfg g_env;
+static std::atomic<int> g_env_ready{0};
+static std::mutex g_env_mutex;
+static int env_int(const char* name)
+{
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : SMK_ENV_UNSET;
+}
+static void env_read_locked()
+{
+    EnvCfg c;
+    c.pdl = env_int("SMK_PDL");
+    c.fused_slice = env_int("SMK_FUSED_SLICE");
+    c.fused_cluster = env_int("SMK_FUSED_CLUSTER");
+    c.jacobi_packed = env_int("SMK_JACOBI_PACKED");
+    c.jacobi_stream = env_int("SMK_JACOBI_STREAM");
+    c.jacobi_tile = env_int("SMK_JACOBI_TILE");
+    c.fdd_bulk = env_int("SMK_FDD_BULK");
+    c.advect_tiled = env_int("SMK_ADVECT_TILED");
+    c.project_fused = env_int("SMK_PROJECT_FUSED");
+    g_env = c;
+    g_env_ready.store(1, std::memory_order_release);
+}
+const EnvCfg& env()
+{
+    if (!g_env_ready.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lock(g_env_mutex);
+        if (!g_env_ready.load(std::memory_order_relaxed)) env_read_locked();
+    }
+    return g_env;
+}
+
 // SMK_PDL=0 switches programmatic dependent launch off; never inside a stream capture (plain kernel nodes there)
 bool pdl_enabled(cudaStream_t s)
 {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("SMK_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }
-    if (!on) return false;
+    if (env().pdl == 0) return false;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     return cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
 }
@@ -129,6 +161,13 @@ int smk_set_device(int32_t device)
 {
     const cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail((int)e, "smk_set_device(%d): %s", device, cudaGetErrorString(e));
+    return SMK_OK;
+}
+
+int smk_reload_env(void)
+{
+    std::lock_guard<std::mutex> lock(g_env_mutex);
+    env_read_locked();
     return SMK_OK;
 }
 
@@ -240,6 +279,9 @@ int smk_advect(const smk_grid_t* g, const float* field, float* out, int32_t rows
     if (field == out) return fail(SMK_EINVAL, "smk_advect: the gather is out of place, field == out");
     if (out == u || out == v) return fail(SMK_EINVAL, "smk_advect: out aliases a velocity input");
     if (rows < 1 || cols < 1 || pitch < cols) return fail(SMK_EINVAL, "smk_advect: bad field shape %d x %d pitch %d", rows, cols, pitch);
+    // the velocities are u[h+1][w], v[h][w+1] by the grid's own definition; a field larger than either would index past them
+    if (rows > g->h + 1 || cols > g->w + 1)
+        return fail(SMK_EINVAL, "smk_advect: a %d x %d field does not fit the %d x %d cell grid (at most %d x %d)", rows, cols, g->h, g->w, g->h + 1, g->w + 1);
     if (frame && (rows != g->h || cols != g->w)) return fail(SMK_EINVAL, "smk_advect: frame output needs a cell-centred field");
     return launch_advect(g, field, out, rows, cols, pitch, stride, u, v, dt, scale, frame, frame_stride, fmul, nullptr, (cudaStream_t)stream);
 }
@@ -253,6 +295,8 @@ int smk_advect_slab(const smk_grid_t* g, const float* field, float* out, int32_t
     if (!field || !out || !u || !v) return fail(SMK_EINVAL, "smk_advect_slab: NULL pointer");
     if (field == out || out == u || out == v) return fail(SMK_EINVAL, "smk_advect_slab: out aliases an input");
     if (rows < 1 || cols < 1 || pitch < cols) return fail(SMK_EINVAL, "smk_advect_slab: bad field shape %d x %d pitch %d", rows, cols, pitch);
+    if (rows > g->h + 1 || cols > g->w + 1)
+        return fail(SMK_EINVAL, "smk_advect_slab: a %d x %d field does not fit the %d x %d cell slab", rows, cols, g->h, g->w);
     if (chk && (!chk->overflow_flag || chk->need_lo > chk->need_hi || chk->valid_lo > chk->valid_hi))
         return fail(SMK_EINVAL, "smk_advect_slab: bad check ranges");
     return launch_advect(g, field, out, rows, cols, pitch, 0, u, v, dt, scale, nullptr, 0, nullptr, chk, (cudaStream_t)stream);
@@ -370,6 +414,14 @@ int smk_div_norms(const smk_grid_t* g, const float* u, const float* v, float* ou
     SMK_TRY(check_ptrs("smk_div_norms", {u, v}));
     if (!out) return fail(SMK_EINVAL, "smk_div_norms: out NULL");
     return launch_div_norms(g, u, v, out, (cudaStream_t)stream);
+}
+
+int smk_jacobi_residual(const smk_grid_t* g, const float* div, const float* p, float* out, void* stream)
+{
+    SMK_TRY(check_grid(g, "smk_jacobi_residual"));
+    SMK_TRY(check_ptrs("smk_jacobi_residual", {div, p}));
+    if (!out) return fail(SMK_EINVAL, "smk_jacobi_residual: out NULL");
+    return launch_jacobi_residual(g, div, p, out, (cudaStream_t)stream);
 }
 
 int smk_fractal_fields(float* perlin, float* mandel, float* mul, int32_t na, int32_t nb, int32_t pitch, float intensity,

@@ -82,6 +82,23 @@ inline void launch_chain(void (*kernel)(P...), const dim3 grid, const dim3 block
     (void)cudaLaunchKernelEx(&cfg, kernel, P(args)...);          // errors are picked up by check_launch()
 }
 
+// Tuning / test switches from the environment, read ONCE per process (getenv is not free and not thread-safe against
+// setenv; a launch must not pay for it) and again only on smk_reload_env(), which the tests call after changing a variable.
+// SMK_ENV_UNSET marks a variable that is not set: the launcher then picks by its own rule.
+constexpr int SMK_ENV_UNSET = -2147483647 - 1;
+struct EnvCfg {
+    int pdl;             // SMK_PDL            0: no programmatic dependent launch
+    int fused_slice;     // SMK_FUSED_SLICE    0: one CTA per simulation, n > 0: time-sliced schedule with pieces of n steps
+    int fused_cluster;   // SMK_FUSED_CLUSTER  0: never split a simulation over a CTA cluster, 2: always (when supported)
+    int jacobi_packed;   // SMK_JACOBI_PACKED  0: scalar in-place kernel, else mask of packed row pairs
+    int jacobi_stream;   // SMK_JACOBI_STREAM  0 off / 1 LDGSTS / 2 TMA staging of the streaming kernel
+    int jacobi_tile;     // SMK_JACOBI_TILE    1: 64 x 128 (8 warps), 2: 128 x 128, 3: 64 x 128 (16 warps)
+    int fdd_bulk;        // SMK_FDD_BULK       0 / 1: staging path of k_forces_diffuse_div
+    int advect_tiled;    // SMK_ADVECT_TILED   0 / 1: direct / shared-memory tiled advection
+    int project_fused;   // SMK_PROJECT_FUSED  0: k_project + k_advect(u) as two kernels even where the fused one applies
+};
+const EnvCfg& env();
+
 // thread-local error string + checks (abi.cu)
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
@@ -108,6 +125,7 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
                   const float* u, const float* v, float dt, float scale, float* frame, int64_t frame_stride,
                   const float* fmul, const smk_slab_check_t* chk, cudaStream_t s);
 int launch_div_norms(const smk_grid_t* g, const float* u, const float* v, float* out, cudaStream_t s);
+int launch_jacobi_residual(const smk_grid_t* g, const float* div, const float* p, float* out, cudaStream_t s);
 int launch_fractal_fields(float* perlin, float* mandel, float* mul, int na, int nb, int pitch, float intensity, int iterations,
                           const float* px, const float* py, const float* mx, const float* my, cudaStream_t s);
 int launch_frame_features(const float* frames, int64_t frame_stride, int nframes, int h, int w, int pitch,

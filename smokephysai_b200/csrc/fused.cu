@@ -67,6 +67,8 @@ struct FusedArgs {
     int K, nsteps;
     const int4* items;                                    // time-sliced schedule (see k_step_fused): (simulation, first step, end step, 0) per CTA, else NULL
     unsigned* progress;                                   // [nsims] steps completed, zeroed before the launch (time-sliced schedule only)
+    unsigned* ticket;                                     // next item of `items` to hand out (zeroed with progress)
+    unsigned spin_budget;                                 // polls a consumer CTA spends on a hand-over before it gives up
 #ifdef SMK_FUSED_TIMING
     long long* ticks;
 #endif
@@ -253,11 +255,18 @@ k_step_fused(const FusedArgs a)
     // (McNaughton's wrap-around rule); a piece is walked from its END, so a simulation cut by a piece boundary is started
     // (steps 0..) as the FIRST item of the lower piece and finished as the LAST item of the next piece, after the first has
     // published the state (progress[b], release / acquire at GPU scope).  Every item is a CTA of its own; the host orders
-    // them by planned start time, and because CTAs are dispatched in index order to SMs as they free up, the execution
-    // follows the plan: an item that waits always waits for a CTA of lower index, which is running or done (no deadlock).
+    // them by planned start time: an item that waits always waits for an item of lower table index (no deadlock, see below).
     // 256 simulations x 20 steps on 148 SMs take 35 step-times instead of 40 that way.
+    // The item is claimed with a ticket (atomicAdd at CTA entry), not read at blockIdx: tickets are handed out in the order
+    // CTAs actually START, so "the item I wait for has a lower ticket" means "its CTA is already running or done" whatever
+    // order the hardware dispatches the grid in (MPS, a co-resident kernel, a future scheduler).
     int4 item = make_int4((int)blockIdx.x, 0, a.nsteps, 0);
-    if (a.items) item = __ldg(a.items + blockIdx.x);
+    if (a.items) {
+        if (threadIdx.x == 0) reinterpret_cast<int*>(sd + FZ_SD)[0] = (int)atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        item = __ldg(a.items + reinterpret_cast<const int*>(sd + FZ_SD)[0]);
+        __syncthreads();                // the halo buffer the ticket travelled through is written again further down
+    }
     const size_t b = (size_t)item.x;
     const int t_begin = item.y, t_end = item.z;
     float* __restrict__ gU = a.U + b * a.su_;
@@ -280,8 +289,12 @@ k_step_fused(const FusedArgs a)
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(a.progress + b) : "memory");
                 if (done < (unsigned)t_begin) {
+                    // Backstop only: the producer holds a lower ticket, so it is resident and this wait ends after at most
+                    // t_begin steps of its work.  The budget grows with that work (about 2^18 polls ~ 0.1 s per awaited
+                    // step-sweep block, floor 2^25 ~ 6 s) so a long K or a slow clock cannot trip it; if it does expire
+                    // the launch fails (sticky error the host sees at its next call) instead of hanging the GPU.
                     __nanosleep(200);
-                    if (++spins > (1u << 25)) __trap();      // > 6 s: the producer CTA never ran -- fail the launch instead of hanging the GPU
+                    if (++spins > a.spin_budget) __trap();
                 }
             } while (done < (unsigned)t_begin);
         }
@@ -626,10 +639,7 @@ static int pick_seg_len(const smk_grid_t* g, int nsteps, const void* scratch, cu
     if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return 0;
     const int64_t total = (int64_t)g->batch * nsteps;
     if (total > 0x3fffffff) return 0;
-    if (const char* e = getenv("SMK_FUSED_SLICE")) {
-        const int v = atoi(e);
-        return v > 0 ? v : 0;
-    }
+    if (env().fused_slice != SMK_ENV_UNSET) return env().fused_slice > 0 ? env().fused_slice : 0;
     int dev = 0, nsm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) return 0;
     if (g->batch <= nsm) return 0;
@@ -696,7 +706,7 @@ int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float*
     a.su_ = g->stride_u; a.sv_ = g->stride_v; a.sc_ = g->stride_c;
     a.frame_step_stride = frame_step_stride; a.frame_batch_stride = frame_batch_stride;
     a.dt = dt; a.c_uv = c_uv; a.c_d = c_d; a.decay = decay; a.K = K; a.nsteps = nsteps;
-    a.items = nullptr; a.progress = nullptr;
+    a.items = nullptr; a.progress = nullptr; a.ticket = nullptr; a.spin_budget = 1u << 25;
     int ctas = g->batch;
     const int seg_len = pick_seg_len(g, nsteps, scratch, s);
     if (seg_len > 0) {
@@ -708,11 +718,14 @@ int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float*
             plan_items(g->batch, nsteps, seg_len, plan);
             plan_key[0] = g->batch; plan_key[1] = nsteps; plan_key[2] = seg_len;
         }
-        const size_t counters = (sizeof(unsigned) * (size_t)g->batch + 15) & ~(size_t)15;
+        const size_t counters = (sizeof(unsigned) * ((size_t)g->batch + 1) + 15) & ~(size_t)15;      // progress[batch], ticket
         const size_t need = counters + sizeof(int4) * plan.size();
         const size_t have = sizeof(float) * (size_t)g->stride_c * (size_t)(g->batch - 1) + sizeof(float) * (size_t)g->h * (size_t)g->pitch_c;
         if (need <= have) {
             a.progress = reinterpret_cast<unsigned*>(scratch);
+            a.ticket = a.progress + g->batch;
+            const unsigned long long work = (unsigned long long)nsteps * (unsigned long long)(K > 0 ? K : 1);
+            a.spin_budget = (unsigned)std::min<unsigned long long>(0xfffffff0ull, std::max<unsigned long long>(1ull << 25, work << 14));
             a.items = reinterpret_cast<const int4*>(reinterpret_cast<char*>(scratch) + counters);
             cudaError_t e = cudaMemsetAsync(a.progress, 0, counters, s);
             // pageable source: the runtime stages the table before it returns, the cached vector may change afterwards

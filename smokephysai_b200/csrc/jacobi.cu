@@ -427,9 +427,8 @@ static int pick_T(const smk_grid_t* g, int K, int TH, int tmax, int sms)
 // sweep of a 128 x 128 tile against 928 all-scalar, 920 all-packed; the in-place k_jacobi needs ~1130).
 static int use_packed()
 {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("SMK_JACOBI_PACKED"); v = e ? atoi(e) : 6; }
-    return v;
+    const int v = env().jacobi_packed;
+    return v == SMK_ENV_UNSET ? 6 : v;
 }
 
 static int sm_count();
@@ -444,7 +443,8 @@ static int sm_count();
 // A tile still costs 2.3 us on top of its sweeps (0.48 us each).
 static int stream_env()
 {
-    if (const char* e = getenv("SMK_JACOBI_STREAM")) return use_packed() != 0 ? atoi(e) : 0;
+    const int v = env().jacobi_stream;
+    if (v != SMK_ENV_UNSET) return use_packed() != 0 ? v : 0;
     return -1;
 }
 
@@ -578,7 +578,7 @@ int launch_jacobi(const smk_grid_t* g, const float* div, float* p, float* scratc
     if (g->w <= 128 && g->h <= 128) return run_cfg<8, 16>(g, div, p, scratch, K, T > 0 ? T : 8, in_scratch, s);
     // large grids: overlapped tiles.  T must leave a positive advance in both directions.
     int tile = 0;                                   // 0 auto, 1: 64 x 128 (8 warps), 2: 128 x 128 (16 warps), 3: 64 x 128 (16 warps)
-    if (const char* e = getenv("SMK_JACOBI_TILE")) tile = atoi(e);
+    if (env().jacobi_tile != SMK_ENV_UNSET) tile = env().jacobi_tile;
     int stream = stream_env();                      // -1 auto, 0 off, 1 LDGSTS, 2 TMA (k_jacobi_stream)
     if (tile == 0) {
         // Many waves of CTAs (>= 4 per SM: 4096^2, or a 1/8 slab of 8192^2): overlap one tile's load / store with another's sweeps.

@@ -227,7 +227,7 @@ int launch_forces_diffuse_div(const smk_grid_t* g, const float* u, const float* 
     dim3 grid((g->w + FTW - 1) / FTW, (g->h + FTH - 1) / FTH, g->batch);
     ProfScope prof_(SMK_PH_FORCES_DIFFUSE_DIV, s);
     int bulk = (int64_t)g->h * g->w * g->batch >= ((int64_t)6 << 20) ? 1 : 0;
-    if (const char* e = getenv("SMK_FDD_BULK")) bulk = atoi(e) != 0;       // tests force either staging path on small grids
+    if (env().fdd_bulk != SMK_ENV_UNSET) bulk = env().fdd_bulk != 0;       // tests force either staging path on small grids
     launch_chain(k_forces_diffuse_div, grid, dim3(FTHREADS), 0, s, u, v, d, uo, vo, dout, div, g->h, g->w, g->pitch_u, g->pitch_v, g->pitch_c,
                                                    g->stride_u, g->stride_v, g->stride_c, dt, c_uv, c_d, bulk);
     return check_launch("k_forces_diffuse_div");
@@ -736,7 +736,7 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
     // the tiled kernel wins on big fields (8192^2: 182 against 229 us), the direct one on small ones (1024^2: 10.0
     // against 10.7 us; equal at 2048^2): -1 picks by size, SMK_ADVECT_TILED = 0 / 1 forces one of them
     int tiled = -1;
-    if (const char* e = getenv("SMK_ADVECT_TILED")) tiled = atoi(e);
+    if (env().advect_tiled != SMK_ENV_UNSET) tiled = env().advect_tiled;
     const bool big = (int64_t)rows * cols * g->batch >= (int64_t)6 << 20;
     if ((tiled == 1 || (tiled == -1 && big)) && (rows + AT_R - 1) / AT_R <= 65535) {
         dim3 tgrid((unsigned)((pitch + AT_C - 1) / AT_C), (unsigned)((rows + AT_R - 1) / AT_R), g->batch);
@@ -854,6 +854,60 @@ int launch_div_norms(const smk_grid_t* g, const float* u, const float* v, float*
     ProfScope prof_(SMK_PH_OTHER, s);
     k_div_norms<<<grid, 256, 0, s>>>(u, v, out, g->h, g->w, g->pitch_u, g->pitch_v, g->stride_u, g->stride_v);
     return check_launch("k_div_norms");
+}
+
+// ---- Jacobi residual: per simulation max|p' - p| and sum (p' - p)^2, p' = one more sweep of navier_stokes.py:139-145
+// over (p, div) -- how far the K sweeps just done are from a fixed point.  Same warp-shuffle + atomic reduction as above.
+__global__ void __launch_bounds__(256)
+k_jacobi_residual(const float* __restrict__ P, const float* __restrict__ DIV, float* __restrict__ out,
+                  const int h, const int w, const int pc, const long long sc_)
+{
+    const size_t b = blockIdx.z;
+    P += b * sc_; DIV += b * sc_;
+    float mx = 0.f, ss = 0.f;
+    for (int i = blockIdx.y; i < h; i += gridDim.y)
+        for (int j = blockIdx.x * 256 + threadIdx.x; j < w; j += gridDim.x * 256) {
+            const float pc0 = P[(size_t)i * pc + j];
+            float pn = 0.f;                                  // the ring is reset to zero by every sweep (:140-141)
+            if (i >= 1 && i <= h - 2 && j >= 1 && j <= w - 2) {
+                float s = P[(size_t)(i - 1) * pc + j] + P[(size_t)(i + 1) * pc + j];
+                s = s + P[(size_t)i * pc + j - 1];
+                s = s + P[(size_t)i * pc + j + 1];
+                pn = 0.25f * (s - DIV[(size_t)i * pc + j]);
+            }
+            const float r = pn - pc0;
+            mx = fmaxf(mx, fabsf(r));
+            ss += r * r;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    __shared__ float smx[8], sss[8];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    if (lane == 0) { smx[wp] = mx; sss[wp] = ss; }
+    __syncthreads();
+    if (wp == 0) {
+        mx = lane < 8 ? smx[lane] : 0.f; ss = lane < 8 ? sss[lane] : 0.f;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        }
+        if (lane == 0) {
+            atomicMax(reinterpret_cast<int*>(out + 2 * b), __float_as_int(mx));
+            atomicAdd(out + 2 * b + 1, ss);
+        }
+    }
+}
+
+int launch_jacobi_residual(const smk_grid_t* g, const float* div, const float* p, float* out, cudaStream_t s)
+{
+    dim3 grid((g->w + 255) / 256, min(g->h, 64), g->batch);
+    ProfScope prof_(SMK_PH_OTHER, s);
+    k_jacobi_residual<<<grid, 256, 0, s>>>(p, div, out, g->h, g->w, g->pitch_c, g->stride_c);
+    return check_launch("k_jacobi_residual");
 }
 
 // ---- a13: FractalGenerator fields (constant per grid shape; computed once and cached by the host) -------

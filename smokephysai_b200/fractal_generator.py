@@ -24,9 +24,9 @@ class FractalGenerator(nn.Module):
         self._cache = {}
 
     def _stream(self):
-        _lib.call("smk_set_device", self._cuda.index)
-        return torch.cuda.current_stream(self._cuda).cuda_stream
+        return _lib.stream_on(self._cuda)
 
+    @_lib.scoped
     def _fields(self, shape, scale=10.0, iterations=100, intensity=0.0, want=("perlin",)):
         """Launch k_fractal_fields for grid shape (h, w); outputs are laid out (w, h) like the reference's meshgrid('ij')."""
         h, w = int(shape[0]), int(shape[1])
@@ -70,6 +70,7 @@ class FractalGenerator(nn.Module):
                                "as in the reference)" % (w, h))
         return self._fields(shape, intensity=intensity, want=("mul",))["mul"]
 
+    @_lib.scoped
     def apply_fractal_perturbation(self, field, intensity=0.1):
         """field + intensity*F*field (fractal_generator.py:53-62)."""
         field_t = torch.as_tensor(field)

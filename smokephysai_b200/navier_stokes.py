@@ -114,6 +114,7 @@ class NavierStokesSimulator(nn.Module):
         self._grid = self._layout.grid_struct()
         self._arena = None
         self._state = State()
+        self._mirrors = {}
         self.setup_grid()
 
     # ------------------------------------------------------------------ state (navier_stokes.py:24-35)
@@ -130,6 +131,7 @@ class NavierStokesSimulator(nn.Module):
                 arr[1] = base + 4 * L.offset[b]
             st.div = base + 4 * L.offset["div"]
         else:
+            self._mirrors.clear()
             self._arena.zero_()
         self._state.cur_u = self._state.cur_v = self._state.cur_d = self._state.cur_p = 0
 
@@ -147,9 +149,32 @@ class NavierStokesSimulator(nn.Module):
 
     def _get(self, k):
         v = self._live(k)
-        return v if self._out_device.type == "cuda" else v.to(self._out_device)
+        if self._out_device.type == "cuda":
+            return v
+        # device='cpu' (benchmark.py:260): the caller gets a host copy.  The reference hands out its LIVE tensor, so
+        # in-place edits (`sim.density[mask] += x`) must not be lost: remember the copy with its version counter and
+        # write it back before the next launch if it was modified (_flush_mirrors).
+        self._flush_mirrors()               # an earlier copy of this field may carry edits that are not on the device yet
+        t = self._live(k).to(self._out_device)
+        self._mirrors[k] = (t, t._version)
+        return t
+
+    def _flush_mirrors(self):
+        """Write host copies that were edited in place since they were handed out back to the device state."""
+        if not self._mirrors:
+            return
+        for k, (t, ver) in self._mirrors.items():
+            if t._version != ver:
+                self._live(k).copy_(t)
+        self._mirrors.clear()
 
     def _set(self, k, value):
+        mirror = self._mirrors.get(k)
+        if mirror is not None and value is mirror[0]:        # `sim.density *= c` on the host copy re-assigns it
+            self._mirrors.pop(k)
+            self._live(k).copy_(value)
+            return
+        self._mirrors.pop(k, None)
         dst = self._live(k)
         if not torch.is_tensor(value):
             value = torch.as_tensor(value, dtype=torch.float32)
@@ -171,8 +196,10 @@ class NavierStokesSimulator(nn.Module):
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
-        _lib.call("smk_set_device", self._cuda.index)
-        return torch.cuda.current_stream(self._cuda).cuda_stream
+        """The stream to launch on.  Also the one place every launch passes through: host copies edited in place are
+        written back here, and the library's (statically linked) CUDA runtime is pointed at this simulator's device."""
+        self._flush_mirrors()
+        return _lib.stream_on(self._cuda)
 
     def _params(self):
         dt, nu = float(self.dt), float(self.viscosity)
@@ -279,6 +306,13 @@ class NavierStokesSimulator(nn.Module):
         vb, Bv, hv, wv, pv = self._stage(v)
         if Bu != B or Bv != B:
             raise ValueError("field, u and v must have the same batch size")
+        # the staggered pair defines the cell grid: u [h+1, w], v [h, w+1] (navier_stokes.py:27-28).  The reference clamps
+        # to whatever shapes it is given; the kernels index u and v by that grid, so anything else is refused, not guessed.
+        if hu != hv + 1 or wv != wu + 1:
+            raise ValueError("advection_step needs u of shape [h+1, w] and v of shape [h, w+1]; got u %s, v %s"
+                             % ((hu, wu), (hv, wv)))
+        if rows > hv + 1 or cols > wu + 1:
+            raise ValueError("advection_step: a %d x %d field does not fit the %d x %d cell grid of u, v" % (rows, cols, hv, wu))
         g = Grid(hv, wu, B, pu, pv, _round4(wu), hu * pu, hv * pv, hv * _round4(wu))
         out = torch.zeros_like(fb)
         _lib.call("smk_advect", C.byref(g), fb.data_ptr(), out.data_ptr(), rows, cols, pitch, rows * pitch,
@@ -395,5 +429,23 @@ class NavierStokesSimulator(nn.Module):
         out[:, 1] = out[:, 1].sqrt()
         return out
 
+    def jacobi_residual_norms(self):
+        """(max|p' - p|, ||p' - p||_2) per simulation, p' = one more Jacobi sweep (navier_stokes.py:139-145) over the live
+        pressure and the divergence of the last projection: [batch, 2] on the host.  Meaningful right after
+        pressure_projection() or a step() of the phase-per-kernel path (the fused kernel keeps the divergence in registers)."""
+        out = torch.zeros(self.batch, 2, dtype=torch.float32, device=self._cuda)
+        _lib.call("smk_jacobi_residual", C.byref(self._grid), self._state.div, self._ptr("p"), out.data_ptr(), self._stream())
+        out = out.cpu().double()
+        out[:, 1] = out[:, 1].sqrt()
+        return out
+
     def forward(self):
         return self.step()
+
+
+# every method that launches runs with the simulator's device current and restores the caller's afterwards
+for _name in ("setup_grid", "add_sources", "splat_uploaded", "upload_sources", "diffusion_step", "advection_step", "_bilerp",
+              "pressure_projection", "step", "step_into", "run_steps", "run_steps_time_major", "divergence_norms",
+              "jacobi_residual_norms", "step_is_fused"):
+    setattr(NavierStokesSimulator, _name, _lib.scoped(getattr(NavierStokesSimulator, _name)))
+del _name

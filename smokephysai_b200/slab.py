@@ -205,6 +205,19 @@ class NcclExchanger:
             _lib.call("smk_nccl_comm_destroy", self.comm)
             self.comm = None
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        try:                                # interpreter shutdown may already have torn torch / the library down
+            self.close()
+        except Exception:
+            pass
+
 
 def default_exchanger(device):
     """NcclExchanger when the default process group runs NCCL on GPUs, else torch.distributed P2P (gloo on CPU)."""
@@ -235,8 +248,10 @@ class SlabNavierStokes:
         H, W = int(grid_size[0]), int(grid_size[1])
         self.T = max(1, int(sweeps_per_launch))
         self.halo = int(halo) if halo is not None else self.T + 4
-        if world > 1 and self.halo < self.T + 3:
-            raise ValueError("halo of %d rows is too shallow for %d fused sweeps per launch (need >= T + 3)" % (self.halo, self.T))
+        if world > 1 and self.halo < self.T + 4:
+            # T rows eroded by the fused sweeps of a launch, 2 by diffusion + divergence, 1 by the gradient subtract and 1 for
+            # the second row of a sub-cell bilinear back-trace; deeper back-traces need halo - 4 >= their reach (check())
+            raise ValueError("halo of %d rows is too shallow for %d fused sweeps per launch (need >= T + 4)" % (self.halo, self.T))
         # deep halo: the pressure ghosts stay exact through all K sweeps, one exchange per step (u, v, density, p)
         self.single_exchange = needs_single_exchange(world, self.halo, jacobi_iters)
         self.geom = SlabGeometry(H, W, world, rank, self.halo if world > 1 else 0)
@@ -381,6 +396,7 @@ class SlabNavierStokes:
     def gather(self, name):
         """All ranks: the global field assembled from every rank's owned rows (torch.distributed all_gather)."""
         import torch.distributed as dist
+        self.check()                       # rows next to a cut are only exact while no back-trace left the halo
         mine = self.owned(name).contiguous()
         if self.world == 1:
             return mine.clone()
@@ -425,6 +441,7 @@ class LocalGroup:
                     p[k][1]()
 
     def gather(self, name):
+        self.check()
         return torch.cat([s.owned(name) for s in self.slabs], dim=0)
 
     def check(self):

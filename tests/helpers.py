@@ -1,5 +1,7 @@
 """Shared helpers for the parity tests."""
+import contextlib
 import hashlib
+import os
 
 import numpy as np
 
@@ -42,3 +44,26 @@ def emitters_for_sequence(s, h=128, w=128):
         inten = float(rng.uniform(0.5, 2.0))
         out.append((x, y, 8, inten))
     return out
+
+
+@contextlib.contextmanager
+def smk_env(**switches):
+    """Set SMK_* switches for the body and make the library re-read them (it reads the environment once per process:
+    include/smoke_b200.h smk_reload_env); restored and re-read on exit.  smk_env(SMK_FUSED_SLICE=3)."""
+    from smokephysai_b200 import _lib
+    saved = {k: os.environ.get(k) for k in switches}
+    for k, v in switches.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = str(v)
+    _lib.reload_env()
+    try:
+        yield
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        _lib.reload_env()

@@ -46,7 +46,8 @@ def test_ctypes_table_matches_header(so_path):
     for name, args in table.items():
         assert len(args) == decl[name], "%s: %d ctypes args vs %d in the header" % (name, len(args), decl[name])
     lib = _lib.load()
-    assert lib.smk_version() == 5
+    want = int(re.search(r"#define SMK_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
+    assert lib.smk_version() == want == 6
     assert isinstance(lib.smk_last_error_string(), bytes)
 
 

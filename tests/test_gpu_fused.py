@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import oracle
-from helpers import assert_same, emitters_for_sequence
+from helpers import assert_same, emitters_for_sequence, smk_env
 
 pytestmark = pytest.mark.gpu
 
@@ -135,7 +135,7 @@ def test_fused_multi_step_launch_equals_single_steps(h, w):
 
 @pytest.mark.parametrize("h,w,B,n,seg", [(128, 128, 5, 7, 3), (128, 128, 5, 7, 9), (128, 128, 4, 6, 1), (60, 128, 6, 5, 4), (128, 52, 3, 8, 5),
                                          (128, 128, 7, 4, 28)])
-def test_fused_time_sliced_schedule_equals_one_cta_per_simulation(h, w, B, n, seg, monkeypatch):
+def test_fused_time_sliced_schedule_equals_one_cta_per_simulation(h, w, B, n, seg):
     """The time-sliced schedule of k_step_fused (a CTA runs `seg` consecutive simulation-steps of the simulation-major
     line and hands a simulation cut by its piece boundary over to the next CTA through global memory) must give the
     frames and fields of the one-CTA-per-simulation schedule bit for bit.  SMK_FUSED_SLICE forces the piece length:
@@ -144,15 +144,15 @@ def test_fused_time_sliced_schedule_equals_one_cta_per_simulation(h, w, B, n, se
     states = [random_state(h, w, 500 + b, vel=150.0) for b in range(B)]
     out = {}
     for mode in ("0", str(seg)):
-        monkeypatch.setenv("SMK_FUSED_SLICE", mode)
-        ns = make(h, w, 0.02, 0.004, K, batch=B, step_kernel="fused")
-        for k in FIELDS:
-            setattr(ns, k, T(np.stack([st[k] for st in states])))
-        fmul = torch.linspace(0.0, 0.05, h * ns._layout.pitch_c, device="cuda").view(h, ns._layout.pitch_c)
-        n0 = _lib.launch_count()
-        frames = ns.run_steps(n, fmul=fmul)
-        assert _lib.launch_count() - n0 == 1
-        out[mode] = (N(frames), {k: N(getattr(ns, k)) for k in FIELDS})
+        with smk_env(SMK_FUSED_SLICE=mode):
+            ns = make(h, w, 0.02, 0.004, K, batch=B, step_kernel="fused")
+            for k in FIELDS:
+                setattr(ns, k, T(np.stack([st[k] for st in states])))
+            fmul = torch.linspace(0.0, 0.05, h * ns._layout.pitch_c, device="cuda").view(h, ns._layout.pitch_c)
+            n0 = _lib.launch_count()
+            frames = ns.run_steps(n, fmul=fmul)
+            assert _lib.launch_count() - n0 == 1
+            out[mode] = (N(frames), {k: N(getattr(ns, k)) for k in FIELDS})
     assert_same(out[str(seg)][0], out["0"][0], "frames, sliced vs classic")
     for k in FIELDS:
         assert_same(out[str(seg)][1][k], out["0"][1][k], k + ", sliced vs classic")
@@ -227,3 +227,33 @@ def test_fused_divergence_extreme_magnitudes(scale):
             a, b, c = N(getattr(fz, k)), getattr(ref, k), N(getattr(ph, k))
             assert np.array_equal(a, b, equal_nan=True), "scale %g step %d %s fused vs oracle" % (scale, t, k)
             assert np.array_equal(c, b, equal_nan=True), "scale %g step %d %s phases vs oracle" % (scale, t, k)
+
+
+def test_fused_time_sliced_hand_over_with_a_co_resident_kernel():
+    """The hand-over of the time-sliced schedule may only ever wait for a CTA that has already started: items are claimed
+    by ticket at CTA entry (fused.cu), so the guarantee does not depend on the order the hardware dispatches the grid in.
+    A long-running kernel on a second stream takes SMs away while run_steps executes (CTAs then start late and out of
+    their planned order); frames and fields must still equal the one-CTA-per-simulation schedule bit for bit."""
+    h = w = 128
+    B, n, K = 40, 6, 8
+    states = [random_state(h, w, 900 + b, vel=100.0) for b in range(B)]
+    out = {}
+    side = torch.cuda.Stream()
+    for mode in ("0", "2"):
+        with smk_env(SMK_FUSED_SLICE=mode):
+            ns = make(h, w, 0.02, 0.004, K, batch=B, step_kernel="fused")
+            for k in FIELDS:
+                setattr(ns, k, T(np.stack([st[k] for st in states])))
+            torch.cuda.synchronize()
+            if mode != "0":
+                with torch.cuda.stream(side):
+                    torch.cuda._sleep(int(2e8))                       # ~0.1 s spin kernel, co-resident with the step kernel
+                    x = torch.randn(4096, 4096, device="cuda")
+                    for _ in range(8):
+                        x = (x @ x).clamp_(-1, 1)                    # and a stream of full-grid kernels competing for SMs
+            frames = ns.run_steps(n)
+            torch.cuda.synchronize()
+            out[mode] = (N(frames), {k: N(getattr(ns, k)) for k in FIELDS})
+    assert_same(out["2"][0], out["0"][0], "frames, sliced under contention vs classic")
+    for k in FIELDS:
+        assert_same(out["2"][1][k], out["0"][1][k], k + ", sliced under contention vs classic")

@@ -15,7 +15,7 @@ import pytest
 import torch
 
 import oracle
-from helpers import assert_same, emitters_for_sequence, nerr, sha
+from helpers import assert_same, emitters_for_sequence, nerr, sha, smk_env
 
 pytestmark = pytest.mark.gpu
 
@@ -405,20 +405,11 @@ def test_jacobi_every_tile_shape_vs_oracle(tile, h, w, K, T_):
     ns._field("div").copy_(T(div))
     st = ns._state
     flag = C.c_int32(0)
-    saved = {k: os.environ.get(k) for k in ("SMK_JACOBI_TILE", "SMK_JACOBI_STREAM")}
     # "stream1/2": the persistent kernel that prefetches the next 128 x 128 tile into shared memory with 16-byte cp.async (1) or
     # with two TMA tensor loads completed on an mbarrier (2); 1500 x 1900 gives its CTAs two tiles each, the others one or none
     # "half-stream1/2": the same kernel on 64 x 128 tiles, two persistent CTAs per SM
-    os.environ["SMK_JACOBI_TILE"] = ("1" if tile.startswith("half") else "2") if stream else str(tile)
-    os.environ["SMK_JACOBI_STREAM"] = str(stream)
-    try:
+    with smk_env(SMK_JACOBI_TILE=("1" if tile.startswith("half") else "2") if stream else str(tile), SMK_JACOBI_STREAM=stream):
         _lib.call("smk_jacobi", C.byref(ns._grid), st.div, st.p[0], st.p[1], K, T_, C.byref(flag), ns._stream())
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
     st.cur_p = flag.value
     assert_same(N(ns.p), oracle.jacobi(p, div, K), "jacobi tile %s" % tile)
 
@@ -436,17 +427,8 @@ def test_jacobi_stream_batched_vs_oracle(stream):
     ns._field("div").copy_(T(div))
     st = ns._state
     flag = C.c_int32(0)
-    saved = {k: os.environ.get(k) for k in ("SMK_JACOBI_TILE", "SMK_JACOBI_STREAM")}
-    os.environ["SMK_JACOBI_TILE"] = "2"
-    os.environ["SMK_JACOBI_STREAM"] = str(stream)
-    try:
+    with smk_env(SMK_JACOBI_TILE=2, SMK_JACOBI_STREAM=stream):
         _lib.call("smk_jacobi", C.byref(ns._grid), st.div, st.p[0], st.p[1], K, 6, C.byref(flag), ns._stream())
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
     st.cur_p = flag.value
     got = N(ns.p)
     for b in range(B):
@@ -461,11 +443,13 @@ def force_advect_kernel():
 
     def set_(v):
         os.environ["SMK_ADVECT_TILED"] = str(v)
+        _lib.reload_env()
     yield set_
     if old is None:
         os.environ.pop("SMK_ADVECT_TILED", None)
     else:
         os.environ["SMK_ADVECT_TILED"] = old
+    _lib.reload_env()
 
 
 @pytest.mark.parametrize("tiled", [0, 1])
@@ -522,9 +506,7 @@ def test_both_advection_kernels_in_slabs(force_advect_kernel, tiled):
 def test_both_staging_paths_of_forces_diffuse_div_vs_oracle(bulk, h, w):
     """k_forces_diffuse_div stages interior tiles with bulk cp.async copies on big grids (SMK_FDD_BULK forces it): both
     paths, on grids that have interior AND edge tiles, against the oracle, bit for bit."""
-    old = os.environ.get("SMK_FDD_BULK")
-    os.environ["SMK_FDD_BULK"] = str(bulk)
-    try:
+    with smk_env(SMK_FDD_BULK=bulk):
         rng = np.random.default_rng(h + w + bulk)
         ref = oracle.OracleSolver((h, w), 0.02, 0.01, 5)
         ref.u = ((rng.random((h + 1, w)) - 0.5) * 40).astype(np.float32)
@@ -539,8 +521,87 @@ def test_both_staging_paths_of_forces_diffuse_div_vs_oracle(bulk, h, w):
             ns.step()
             for k in ("u", "v", "p", "density"):
                 assert_same(N(getattr(ns, k)), getattr(ref, k), "%dx%d bulk %d step %d %s" % (h, w, bulk, t, k))
-    finally:
-        if old is None:
-            del os.environ["SMK_FDD_BULK"]
-        else:
-            os.environ["SMK_FDD_BULK"] = old
+
+
+def test_jacobi_residual_norms_vs_oracle():
+    """north_star: warp-shuffle reductions for the residual norm.  smk_jacobi_residual = max and L2 of p' - p, p' one more
+    sweep of navier_stokes.py:139-145 over the pressure and divergence the projection just used."""
+    h, w, K = 96, 160, 20
+    rng = np.random.default_rng(5)
+    u = ((rng.random((h + 1, w)) - 0.5) * 2).astype(np.float32)
+    v = ((rng.random((h, w + 1)) - 0.5) * 2).astype(np.float32)
+    p0 = rng.standard_normal((h, w)).astype(np.float32)
+    ns = make(h, w, K=K)
+    ns.u, ns.v, ns.p = T(u), T(v), T(p0)
+    ns.pressure_projection()
+    got = ns.jacobi_residual_norms()[0].numpy()
+    div = oracle.divergence(u, v, 0.01)
+    pK = oracle.jacobi(p0, div, K)
+    assert_same(N(ns.p), pK, "p after K sweeps")
+    r = (oracle.jacobi(pK, div, 1) - pK).astype(np.float32)            # fp32 difference, as the kernel forms it
+    assert got[0] == np.abs(r).max()                                   # the max is exact
+    l2 = np.sqrt((r.astype(np.float64) ** 2).sum())
+    assert abs(got[1] - l2) <= 1e-5 * l2                               # fp32 partial sums in a different order: 1e-5 relative
+    # more sweeps bring the iteration closer to its fixed point
+    ns2 = make(h, w, K=4 * K)
+    ns2.u, ns2.v, ns2.p = T(u), T(v), T(p0)
+    ns2.pressure_projection()
+    assert ns2.jacobi_residual_norms()[0, 1] < got[1]
+
+
+def test_advection_step_refuses_shapes_it_would_read_out_of_bounds():
+    """the hook builds the cell grid from v's rows and u's columns; anything inconsistent is refused."""
+    ns = make(16, 20)
+    u, v = torch.zeros(17, 20), torch.zeros(16, 21)
+    ns.advection_step(torch.zeros(17, 20), u, v)                       # u-shaped, v-shaped and cell-centred fields are fine
+    ns.advection_step(torch.zeros(16, 21), u, v)
+    with pytest.raises(ValueError):
+        ns.advection_step(torch.zeros(16, 20), torch.zeros(16, 20), v)   # u without its staggered row
+    with pytest.raises(ValueError):
+        ns.advection_step(torch.zeros(16, 20), u, torch.zeros(16, 20))   # v without its staggered column
+    with pytest.raises(ValueError):
+        ns.advection_step(torch.zeros(18, 20), u, v)                     # a field taller than u
+    g = _lib.Grid(16, 20, 1, 20, 24, 20, 17 * 20, 16 * 24, 16 * 20, 0, 0)
+    buf = torch.zeros(4096, device="cuda")
+    rc = _lib.load().smk_advect(C.byref(g), buf.data_ptr(), buf.data_ptr() + 8192, 18, 20, 20, 0, buf.data_ptr(), buf.data_ptr(),
+                                0.01, 1.0, None, 0, None, None)
+    assert rc == -1 and b"does not fit" in _lib.load().smk_last_error_string()
+
+
+def test_cpu_output_device_writes_in_place_edits_through():
+    """with device='cpu' (benchmark.py:260) the field properties hand out host copies; in-place edits of those
+    copies -- which work on the reference's live tensors -- must reach the device state before the next launch."""
+    a = NavierStokesSimulator((32, 32), 0.01, 0.001, "cpu")
+    b = NavierStokesSimulator((32, 32), 0.01, 0.001, "cuda")
+    a.add_smoke_source(16, 16, 6, 1.0)
+    b.add_smoke_source(16, 16, 6, 1.0)
+    d = a.density
+    assert d.device.type == "cpu"
+    d[4:8, 4:8] += 2.0                                                 # in place on the host copy
+    b.density[4:8, 4:8] += 2.0                                         # in place on the live view
+    a.u[3, :] = 0.5
+    b.u[3, :] = 0.5
+    dens = a.density
+    dens *= 0.5                                                        # augmented assignment on a fetched copy
+    b.density *= 0.5
+    fa, fb = a.step(), b.step()
+    assert fa.device.type == "cpu"
+    assert_same(N(fa), N(fb), "frame after in-place host edits")
+    for k in ("u", "v", "p", "density"):
+        assert_same(N(getattr(a, k)), N(getattr(b, k)), k)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_simulator_on_another_device_leaves_the_current_device_alone():
+    """a simulator on cuda:1 must not change the process's current device (the library's own CUDA runtime and
+    torch's share the driver's current context)."""
+    torch.cuda.set_device(0)
+    sim = SmokeSimulator((64, 64), device="cuda:1")
+    sim.add_incense_source([(32, 32)], [1.0])
+    f = sim.simulate_step()
+    assert torch.cuda.current_device() == 0 and f.device.index == 1
+    x = torch.ones(4, device="cuda")                                   # default-device allocation still lands on cuda:0
+    assert x.device.index == 0
+    ref = SmokeSimulator((64, 64), device="cuda:0")
+    ref.add_incense_source([(32, 32)], [1.0])
+    assert_same(N(f), N(ref.simulate_step()), "cuda:1 vs cuda:0")
