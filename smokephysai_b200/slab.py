@@ -158,6 +158,8 @@ class NcclExchanger:
     which bound the 8-GPU step (tools/slab_host_time.py).  The 128-byte NCCL id travels over the existing
     torch.distributed group; construction is collective (every rank of the group must build one)."""
 
+    description = "NCCL send/recv over NVLink, one ncclGroup per exchange issued from C (smk_nccl_exchange)"
+
     def __init__(self, device, group=None):
         import torch.distributed as dist
         self.device = torch.device(device)
@@ -219,7 +221,7 @@ class NcclExchanger:
             pass
 
 
-def default_exchanger(device):
+def default_exchanger(device, exchange="auto"):
     """NcclExchanger when the default process group runs NCCL on GPUs, else torch.distributed P2P (gloo on CPU)."""
     import torch.distributed as dist
     if dist.is_initialized() and dist.get_backend() == "nccl" and torch.device(device).type == "cuda":
@@ -243,7 +245,7 @@ class SlabNavierStokes:
     """One rank's slab of a NavierStokesSimulator (navier_stokes.py:6-173 semantics on the global grid)."""
 
     def __init__(self, grid_size, dt=0.01, viscosity=0.001, device="cuda", *, rank, world, jacobi_iters=20,
-                 sweeps_per_launch=10, halo=None, exchanger=None):
+                 sweeps_per_launch=10, halo=None, exchanger=None, exchange="auto"):
         from .navier_stokes import NavierStokesSimulator
         H, W = int(grid_size[0]), int(grid_size[1])
         self.T = max(1, int(sweeps_per_launch))
@@ -260,7 +262,9 @@ class SlabNavierStokes:
         self.rank, self.world = int(rank), int(world)
         self.local = NavierStokesSimulator((self.geom.hl, W), dt, viscosity, device, jacobi_iters=jacobi_iters,
                                            sweeps_per_launch=self.T, _slab=(self.geom.A, H))
-        self.exchanger = exchanger if exchanger is not None else (default_exchanger(self.local._cuda) if world > 1 else None)
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl', got %r" % (exchange,))
+        self.exchanger = exchanger if exchanger is not None else (default_exchanger(self.local._cuda, exchange) if world > 1 else None)
         self._overflow = torch.zeros(1, dtype=torch.int32, device=self.local._cuda)
         self.steps_done = 0
 
@@ -364,6 +368,14 @@ class SlabNavierStokes:
                 self.exchanger.exchange(self.geom, self.exchange_list(arg))
             else:
                 arg()
+
+    def exchange_description(self):
+        """One line for logs / bench output: how the ghost rows travel."""
+        if self.world == 1 or not self.exchanger:
+            return "no exchange"
+        plan = ("ONE exchange per step (u, v, density, p)" if self.single_exchange
+                else "u, v, density once per step and p after every launch of <= %d fused sweeps" % self.T)
+        return "%s: %s" % (getattr(self.exchanger, "description", type(self.exchanger).__name__), plan)
 
     def capture(self, nsteps=1):
         """Record `nsteps` consecutive steps -- kernels and NCCL halo exchanges -- into a CUDA graph and return it

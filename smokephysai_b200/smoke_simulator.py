@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import chaos
+from . import chaos, hostmem
 from .fractal_generator import FractalGenerator
 from .navier_stokes import NavierStokesSimulator
 
@@ -72,7 +72,10 @@ class SmokeSimulator(nn.Module):
         key = (T,)
         if getattr(self, "_gen_key", None) != key:
             self._gen_dev = torch.empty(T, B, L.h, L.pitch_c, dtype=torch.float32, device=ns._cuda)
-            self._gen_host = torch.empty(T, B, L.h, L.pitch_c, dtype=torch.float32).pin_memory()
+            # pinned pages on the NUMA node of this GPU's PCIe root: with several ranks copying at once a buffer on the far
+            # socket costs most of the D2H bandwidth (hostmem.py)
+            self._gen_host = hostmem.pinned_empty((T, B, L.h, L.pitch_c), torch.float32, ns._cuda)
+            self._gen_host_node = hostmem.gpu_locality(ns._cuda)[0]
             self._gen_copy_stream = torch.cuda.Stream(device=ns._cuda)
             self._gen_key = key
         dev, host, cs = self._gen_dev, self._gen_host, self._gen_copy_stream
