@@ -124,7 +124,8 @@ SMK_API int smk_reload_env(void);
  * profile.  Process-wide, not re-entrant; off by default (no events, no overhead). */
 enum {
     SMK_PH_SPLAT = 0, SMK_PH_FORCES_DIFFUSE_DIV, SMK_PH_JACOBI, SMK_PH_PROJECT,
-    SMK_PH_ADVECT_U, SMK_PH_ADVECT_V, SMK_PH_ADVECT_D, SMK_PH_OTHER, SMK_PH_STEP_FUSED, SMK_PH_COUNT
+    SMK_PH_ADVECT_U, SMK_PH_ADVECT_V, SMK_PH_ADVECT_D, SMK_PH_OTHER, SMK_PH_STEP_FUSED, SMK_PH_HALO, SMK_PH_PROJECT_ADVECT_U,
+    SMK_PH_COUNT
 };
 SMK_API int smk_profile_begin(int32_t max_records);
 SMK_API int smk_profile_end(double* ms_per_phase_host, int64_t* launches_per_phase_host, int32_t nphases);
@@ -245,6 +246,44 @@ SMK_API int smk_nccl_unique_id(void* id128_host);
 SMK_API int smk_nccl_comm_init(const void* id128_host, int32_t rank, int32_t world, void** comm_out_host);
 SMK_API int smk_nccl_comm_destroy(void* comm);
 SMK_API int smk_nccl_exchange(void* comm, const smk_halo_block_t* blocks_host, int32_t nblocks, void* stream);
+
+/* ---- slab halo exchange by direct peer stores over NVLink, and the slab step issued from C (csrc/peer_halo.cu) -----------
+ * Every rank owns a mailbox in device memory: for each of its two neighbours two slots (exchange number & 1) of four field
+ * regions (u, v, density, p; field_stride elements apart), and one arrival counter per neighbour.  The mailbox is exported
+ * with smk_ipc_export, the 64-byte handle travels over the host's own channel (torch.distributed), the neighbours map it with
+ * smk_ipc_open.  smk_peer_push copies this rank's boundary rows into the neighbours' mailboxes (16-byte peer stores) and bumps
+ * their counters (st.release.sys); smk_peer_unpack waits for this rank's counters (ld.acquire.sys) and copies its mailbox
+ * slots into the ghost rows.  link[0] is the upper neighbour (rank - 1), link[1] the lower one (rank + 1); a side without a
+ * neighbour has remote_mailbox == NULL.  Offsets and counts are in fp32 elements relative to the base of the field, multiples
+ * of 4 (whole rows of a pitch that is a multiple of 4); field order u, v, density, p.  seq points at two zero-initialised
+ * uint32 in this rank's memory (exchanges completed; scratch).  All ranks must issue the same sequence of exchanges. */
+typedef struct smk_peer_link {
+    float* remote_mailbox;      /* the neighbour's region that receives FROM this rank, slot 0 (peer-mapped)         */
+    uint32_t* remote_flag;      /* the neighbour's counter this rank bumps after a push (peer-mapped)                */
+    float* local_mailbox;       /* this rank's region that receives from that neighbour, slot 0                      */
+    uint32_t* local_flag;       /* this rank's counter that neighbour bumps                                          */
+    int64_t send_off[4], send_count[4];   /* rows this rank owns that the neighbour stores as ghost rows             */
+    int64_t recv_off[4], recv_count[4];   /* this rank's ghost rows on that side                                     */
+} smk_peer_link_t;
+typedef struct smk_peer_comm {
+    smk_peer_link_t link[2];
+    int64_t field_stride;       /* elements between the field regions of a slot (>= the largest count)               */
+    int64_t parity_stride;      /* elements between the two slots of a region (>= 4 * field_stride)                  */
+    uint32_t* seq;
+} smk_peer_comm_t;
+/*     handle + byte offset of `ptr` inside its device allocation (cudaIpcGetMemHandle works on allocation bases) */
+SMK_API int smk_ipc_export(const void* ptr, void* handle64_host, int64_t* offset_host);
+SMK_API int smk_ipc_open(const void* handle64_host, int64_t offset, void** ptr_out_host);
+SMK_API int smk_ipc_close(void* ptr, int64_t offset);
+/*     field_base_host[4]: device pointers of the live u, v, density, p of this rank; NULL entries are not exchanged */
+SMK_API int smk_peer_push(const smk_peer_comm_t* c, float* const* field_base_host, void* stream);
+SMK_API int smk_peer_unpack(const smk_peer_comm_t* c, float* const* field_base_host, void* stream);
+/* One step() (navier_stokes.py:151-173) of a row slab in a single call: [peer exchange of u, v, density, p when comm != NULL],
+ *     forces + diffusion + divergence, the Jacobi launches, gradient subtract, the three advections with their reach guards
+ *     (chk_* may be NULL).  With comm the caller's halo must be at least jacobi_iters + 4 rows (one exchange per step).  comm == NULL
+ *     steps a slab whose ghost rows the caller refreshed itself, or an undecomposed grid (gh == 0). */
+SMK_API int smk_slab_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, const smk_peer_comm_t* comm,
+                          const smk_slab_check_t* chk_u, const smk_slab_check_t* chk_v, const smk_slab_check_t* chk_d, void* stream);
 
 #ifdef __cplusplus
 }

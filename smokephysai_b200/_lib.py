@@ -45,6 +45,15 @@ class HaloBlock(C.Structure):                # smk_halo_block_t
     _fields_ = [("ptr", c_p), ("count", c_i64), ("peer", c_i32), ("is_send", c_i32)]
 
 
+class PeerLink(C.Structure):                 # smk_peer_link_t
+    _fields_ = [("remote_mailbox", c_p), ("remote_flag", c_p), ("local_mailbox", c_p), ("local_flag", c_p),
+                ("send_off", c_i64 * 4), ("send_count", c_i64 * 4), ("recv_off", c_i64 * 4), ("recv_count", c_i64 * 4)]
+
+
+class PeerComm(C.Structure):                 # smk_peer_comm_t
+    _fields_ = [("link", PeerLink * 2), ("field_stride", c_i64), ("parity_stride", c_i64), ("seq", c_p)]
+
+
 GP, SP, PP = C.POINTER(Grid), C.POINTER(State), C.POINTER(Params)
 
 # name -> argtypes; every function returns int except smk_last_error_string.  Kept in one table so
@@ -81,6 +90,12 @@ SIGNATURES = {
     "smk_nccl_comm_init": [c_p, c_i32, c_i32, C.POINTER(c_p)],
     "smk_nccl_comm_destroy": [c_p],
     "smk_nccl_exchange": [c_p, C.POINTER(HaloBlock), c_i32, c_p],
+    "smk_ipc_export": [c_p, c_p, C.POINTER(c_i64)],
+    "smk_ipc_open": [c_p, c_i64, C.POINTER(c_p)],
+    "smk_ipc_close": [c_p, c_i64],
+    "smk_peer_push": [C.POINTER(PeerComm), C.POINTER(c_p), c_p],
+    "smk_peer_unpack": [C.POINTER(PeerComm), C.POINTER(c_p), c_p],
+    "smk_slab_step": [GP, SP, PP, C.POINTER(PeerComm), C.POINTER(SlabCheck), C.POINTER(SlabCheck), C.POINTER(SlabCheck), c_p],
 }
 
 _lib = None
@@ -186,7 +201,8 @@ def launch_count():
     return n.value
 
 
-PHASES = ("splat", "forces_diffuse_div", "jacobi", "project", "advect_u", "advect_v", "advect_d", "other", "step_fused")
+PHASES = ("splat", "forces_diffuse_div", "jacobi", "project", "advect_u", "advect_v", "advect_d", "other", "step_fused", "halo",
+          "project_advect_u")
 
 
 def profile_begin(max_records=4096):

@@ -221,11 +221,153 @@ class NcclExchanger:
             pass
 
 
+FIELD_ORDER = ("u", "v", "d", "p")          # smk_peer_comm_t field order
+
+
+class PeerExchanger:
+    """Halo exchange by direct peer stores over NVLink (include/smoke_b200.h: smk_peer_*, csrc/peer_halo.cu).
+
+    Every rank owns a mailbox tensor -- per neighbour two slots (exchange number & 1) of four field regions, plus the
+    arrival counters -- exports it once with CUDA IPC (the 64-byte handle travels over the existing torch.distributed
+    group) and maps its neighbours'.  An exchange is two small kernels on the caller's stream: push (boundary rows ->
+    the neighbours' mailboxes, then st.release.sys on their counters) and unpack (ld.acquire.sys on the own counters,
+    mailbox -> ghost rows); no NCCL proxy, no host round trip, capturable in a CUDA graph.  With a halo of at least
+    K + 4 rows SlabNavierStokes.step() hands the whole step, exchange included, to ONE C call (smk_slab_step)."""
+    description = ("direct peer stores into the neighbour's mailbox over NVLink (CUDA IPC mapping, st.release.sys / ld.acquire.sys "
+                   "counters), two kernels per exchange (smk_peer_push / smk_peer_unpack)")
+    NCOUNTERS = 64                          # uint32 slots behind the mailbox: [0..1] arrival counters, [2..3] seq
+
+    def __init__(self, device, geom, layout, group=None, _bases=None):
+        self.device = torch.device(device)
+        self.geom, self.group = geom, group
+        self.pitch = {"u": layout.pitch_u, "v": layout.pitch_v, "d": layout.pitch_c, "p": layout.pitch_c}
+        # all ranks use the same region size so that a rank can address its neighbour's mailbox without asking
+        self.field_stride = (geom.halo + 1) * max(self.pitch.values())
+        self.parity_stride = 4 * self.field_stride
+        self.region = 2 * self.parity_stride                # floats per neighbour: two slots
+        self.buf = torch.zeros(2 * self.region + self.NCOUNTERS, dtype=torch.float32, device=self.device)
+        self._opened = []
+        self.comm = None
+        if _bases is not None:                              # all slabs in one process (tests, LocalGroup): plain pointers
+            self.wire(_bases)
+        elif geom.world > 1:
+            self._wire_ipc()
+
+    # -- addresses inside a mailbox tensor (the same on every rank) ---------------------------------------------------
+    def _region(self, base, side):
+        return base + 4 * side * self.region
+
+    def _counter(self, base, k):
+        return base + 4 * (2 * self.region + k)
+
+    def _wire_ipc(self):
+        import torch.distributed as dist
+        _lib.call("smk_set_device", self.device.index)     # the library's own CUDA runtime must be on this rank's device
+        handle = torch.zeros(72, dtype=torch.uint8)
+        off = C.c_int64(0)
+        _lib.call("smk_ipc_export", self.buf.data_ptr(), handle.data_ptr(), C.byref(off))
+        handle[64:72] = torch.frombuffer(bytearray(C.string_at(C.byref(off), 8)), dtype=torch.uint8)
+        world = dist.get_world_size(self.group)
+        on_gpu = dist.get_backend(self.group) == "nccl"
+        mine = handle.to(self.device) if on_gpu else handle
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine, group=self.group)
+        bases = {}
+        for peer in (self.geom.rank - 1, self.geom.rank + 1):
+            if 0 <= peer < world:
+                h = every[peer].cpu().contiguous()
+                poff = int.from_bytes(bytes(h[64:72].tolist()), "little", signed=True)
+                ptr = C.c_void_p()
+                _lib.call("smk_ipc_open", h.data_ptr(), poff, C.byref(ptr))
+                self._opened.append((ptr.value, poff))
+                bases[peer] = ptr.value
+        self.wire(bases)
+        dist.barrier(group=self.group)                      # nobody pushes before every mapping exists
+
+    def wire(self, bases):
+        """bases: {neighbour rank: address of its mailbox tensor as seen from this process}."""
+        g, mine = self.geom, self.buf.data_ptr()
+        comm = _lib.PeerComm()
+        comm.field_stride, comm.parity_stride = self.field_stride, self.parity_stride
+        comm.seq = self._counter(mine, 2)
+        for side, peer in ((0, g.rank - 1), (1, g.rank + 1)):
+            link = comm.link[side]
+            if peer not in bases:
+                continue
+            # this rank is the LOWER neighbour of rank - 1 (its side 1) and the UPPER neighbour of rank + 1 (its side 0)
+            link.remote_mailbox = self._region(bases[peer], 1 - side)
+            link.remote_flag = self._counter(bases[peer], 1 - side)
+            link.local_mailbox = self._region(mine, side)
+            link.local_flag = self._counter(mine, side)
+            for f, name in enumerate(FIELD_ORDER):
+                sends, recvs = g.blocks("u" if name == "u" else "c")
+                pitch = self.pitch[name]
+                for p_, a, n in sends:
+                    if p_ == peer:
+                        link.send_off[f], link.send_count[f] = a * pitch, n * pitch
+                for p_, a, n in recvs:
+                    if p_ == peer:
+                        link.recv_off[f], link.recv_count[f] = a * pitch, n * pitch
+        self.comm = comm
+
+    def _bases(self, named):
+        arr = (C.c_void_p * 4)()
+        for t, name in named:
+            arr[FIELD_ORDER.index(name)] = t.data_ptr()
+        return arr
+
+    def push(self, named):
+        _lib.call("smk_peer_push", C.byref(self.comm), self._bases(named), torch.cuda.current_stream(self.device).cuda_stream)
+
+    def unpack(self, named):
+        _lib.call("smk_peer_unpack", C.byref(self.comm), self._bases(named), torch.cuda.current_stream(self.device).cuda_stream)
+
+    def exchange_named(self, named):
+        """named: list of (contiguous [rows, pitch] tensor, field name in u / v / d / p)."""
+        arr = self._bases(named)
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.call("smk_peer_push", C.byref(self.comm), arr, s)
+        _lib.call("smk_peer_unpack", C.byref(self.comm), arr, s)
+
+    def close(self):
+        if self._opened:
+            torch.cuda.synchronize(self.device)
+            for ptr, off in self._opened:
+                _lib.call("smk_ipc_close", ptr, off)
+            self._opened = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def peer_exchange_possible(device, group=None):
+    """True when this rank can map both neighbours' memory: one process per GPU on one node, peer access between the
+    GPUs of adjacent ranks (every rank must agree, so the answer is all-reduced)."""
+    import torch.distributed as dist
+    dev = torch.device(device)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ok = 1 if torch.cuda.device_count() >= world else 0
+    if ok:
+        for peer in (rank - 1, rank + 1):
+            if 0 <= peer < world and not torch.cuda.can_device_access_peer(dev.index, (dev.index - rank + peer) % torch.cuda.device_count()):
+                ok = 0
+    t = torch.tensor([ok], dtype=torch.int32, device=dev if dist.get_backend(group) == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))
+
+
 def default_exchanger(device, exchange="auto"):
     """NcclExchanger when the default process group runs NCCL on GPUs, else torch.distributed P2P (gloo on CPU)."""
     import torch.distributed as dist
     if dist.is_initialized() and dist.get_backend() == "nccl" and torch.device(device).type == "cuda":
+        if exchange == "peer" or (exchange == "auto" and peer_exchange_possible(device)):
+            return "peer"                   # built by SlabNavierStokes once the geometry and layout exist
         return NcclExchanger(device)
+    if exchange == "peer":
+        raise RuntimeError("exchange='peer' needs one process per GPU under an NCCL process group")
     return DistExchanger()
 
 
@@ -265,6 +407,20 @@ class SlabNavierStokes:
         if exchange not in ("auto", "peer", "nccl"):
             raise ValueError("exchange must be 'auto', 'peer' or 'nccl', got %r" % (exchange,))
         self.exchanger = exchanger if exchanger is not None else (default_exchanger(self.local._cuda, exchange) if world > 1 else None)
+        if isinstance(self.exchanger, str) and self.exchanger == "peer":
+            try:
+                self.exchanger = PeerExchanger(self.local._cuda, self.geom, self.local._layout)
+                ok = 1
+            except _lib.SmokeLibraryError:
+                if exchange == "peer":
+                    raise
+                ok = 0
+            if exchange == "auto":          # every rank must end up with the same kind of exchanger
+                import torch.distributed as dist
+                t = torch.tensor([ok], dtype=torch.int32, device=self.local._cuda)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                if not int(t.item()):
+                    self.exchanger = NcclExchanger(self.local._cuda)
         self._overflow = torch.zeros(1, dtype=torch.int32, device=self.local._cuda)
         self.steps_done = 0
 
@@ -361,11 +517,32 @@ class SlabNavierStokes:
     def exchange_list(self, names):
         return [(self.full(n), self._kind(n)) for n in names]
 
+    def exchange(self, names):
+        """Refresh the ghost rows of the named fields (u / v / d / p) from both neighbours."""
+        if isinstance(self.exchanger, PeerExchanger):
+            self.exchanger.exchange_named([(self.full(n), n) for n in names])
+        else:
+            self.exchanger.exchange(self.geom, self.exchange_list(names))
+
+    def _c_step(self):
+        """The whole step in one C call (smk_slab_step): peer exchange, forces / diffusion / divergence, Jacobi launches,
+        gradient subtract, the three advections.  Same kernels, same order as the plan below."""
+        ns, g = self.local, self.geom
+        prm = ns._params()
+        chk = [self._check(rows) for rows in (g.hl + 1, g.hl, g.hl)]
+        ref = [C.byref(c) if c is not None else None for c in chk]
+        comm = C.byref(self.exchanger.comm) if isinstance(self.exchanger, PeerExchanger) else None
+        _lib.call("smk_slab_step", self._g(), C.byref(ns._state), C.byref(prm), comm, ref[0], ref[1], ref[2], ns._stream())
+        self.steps_done += 1
+
     def step(self):
         """One time step of this rank's slab (all ranks must call it together)."""
+        if self.world == 1 or (isinstance(self.exchanger, PeerExchanger) and self.single_exchange and self.exchanger.comm is not None
+                               and not getattr(self, "_phase_by_phase", False)):
+            return self._c_step()
         for kind, arg in self.step_plan():
             if kind == "x":
-                self.exchanger.exchange(self.geom, self.exchange_list(arg))
+                self.exchange(arg)
             else:
                 arg()
 
@@ -428,10 +605,21 @@ class LocalGroup:
     """All `world` slabs of one grid in this process on one GPU, stepped in lockstep with in-process halo
     copies: the single-GPU emulation of the multi-GPU run (tests; bit-identical to the undecomposed solver)."""
 
-    def __init__(self, grid_size, dt=0.01, viscosity=0.001, device="cuda", *, world, jacobi_iters=20, sweeps_per_launch=10, halo=None):
+    def __init__(self, grid_size, dt=0.01, viscosity=0.001, device="cuda", *, world, jacobi_iters=20, sweeps_per_launch=10, halo=None,
+                 peer=False):
         self.slabs = [SlabNavierStokes(grid_size, dt, viscosity, device, rank=r, world=world, jacobi_iters=jacobi_iters,
                                        sweeps_per_launch=sweeps_per_launch, halo=halo, exchanger=False) for r in range(world)]
         self.world = world
+        self.peer = bool(peer)
+        if self.peer:
+            # the kernels of the peer exchange with "remote" pointers that are plain pointers into the other slabs' mailboxes:
+            # pushes of all slabs first, then the unpacks (one stream: an unpack waits for pushes that must already be queued)
+            for s in self.slabs:
+                s.exchanger = PeerExchanger(s.local._cuda, s.geom, s.local._layout, _bases={})
+                s._phase_by_phase = True
+            bases = {r: s.exchanger.buf.data_ptr() for r, s in enumerate(self.slabs)}
+            for s in self.slabs:
+                s.exchanger.wire({p: bases[p] for p in (s.rank - 1, s.rank + 1) if 0 <= p < world})
 
     def scatter(self, name, global_field):
         for s in self.slabs:
@@ -447,7 +635,13 @@ class LocalGroup:
             kind = plans[0][k][0]
             if kind == "x":
                 names = plans[0][k][1]
-                local_exchange([s.geom for s in self.slabs], [s.exchange_list(names) for s in self.slabs])
+                if self.peer:
+                    for s in self.slabs:
+                        s.exchanger.push([(s.full(n), n) for n in names])
+                    for s in self.slabs:
+                        s.exchanger.unpack([(s.full(n), n) for n in names])
+                else:
+                    local_exchange([s.geom for s in self.slabs], [s.exchange_list(names) for s in self.slabs])
             else:
                 for p in plans:
                     p[k][1]()

@@ -13,8 +13,9 @@ from helpers import assert_same
 from test_slab_host import random_state, reference_run
 
 pytestmark = pytest.mark.gpu
+PeerSeqOffset = 64          # PeerExchanger.NCOUNTERS: the uint32 counters sit behind the mailbox regions
 
-from smokephysai_b200 import NavierStokesSimulator  # noqa: E402
+from smokephysai_b200 import NavierStokesSimulator, _lib  # noqa: E402
 from smokephysai_b200.slab import LocalGroup, SlabNavierStokes  # noqa: E402
 
 
@@ -100,10 +101,13 @@ def _nccl_worker(rank, world, port, H, W, K, T, steps, out_dir, exch):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         st0 = random_state(H, W, seed=21)
-        from smokephysai_b200.slab import DistExchanger, NcclExchanger
-        slab = SlabNavierStokes((H, W), 0.02, 0.01, "cuda:%d" % rank, rank=rank, world=world, jacobi_iters=K, sweeps_per_launch=T,
-                                exchanger=DistExchanger() if exch == "torch" else None)
-        assert isinstance(slab.exchanger, DistExchanger if exch == "torch" else NcclExchanger)
+        from smokephysai_b200.slab import DistExchanger, NcclExchanger, PeerExchanger
+        halo = K + 4 if exch == "peer-one-call" else None
+        slab = SlabNavierStokes((H, W), 0.02, 0.01, "cuda:%d" % rank, rank=rank, world=world, jacobi_iters=K, sweeps_per_launch=T, halo=halo,
+                                exchanger=DistExchanger() if exch == "torch" else None,
+                                exchange="peer" if exch.startswith("peer") else "nccl")
+        assert isinstance(slab.exchanger, {"torch": DistExchanger, "library": NcclExchanger}.get(exch, PeerExchanger))
+        assert slab.single_exchange == (exch == "peer-one-call")
         for k in ("u", "v", "p", "d"):
             slab.scatter(k, st0[k])
         for _ in range(steps):
@@ -118,10 +122,11 @@ def _nccl_worker(rank, world, port, H, W, K, T, steps, out_dir, exch):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("exch", ["library", "torch"])
+@pytest.mark.parametrize("exch", ["library", "torch", "peer", "peer-one-call"])
 def test_nccl_slabs_match_undecomposed(tmp_path, exch):
-    """Real NCCL over NVLink: halo exchange through the library's own communicator (smk_nccl_exchange, the default) and
-    through torch.distributed P2P ops; both must reproduce the undecomposed run bit for bit."""
+    """Real NVLink: halo exchange through the library's own NCCL communicator (smk_nccl_exchange), through torch.distributed
+    P2P ops, and by direct peer stores into IPC-mapped mailboxes (smk_peer_push / smk_peer_unpack; "peer-one-call": deep halo,
+    the whole step issued by smk_slab_step); every one must reproduce the undecomposed run bit for bit."""
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -168,3 +173,48 @@ def test_full_size_c4_slabs_equal_undecomposed():
             assert torch.equal(got[:, :want[k].shape[1]], want[k]), "%s differs (halo %r)" % (k, halo)
         del grp
         torch.cuda.empty_cache()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("world,H,W,K,T,halo", [(2, 200, 132, 8, 4, None), (3, 300, 260, 12, 6, 16), (4, 512, 384, 20, 10, None),
+                                                (8, 1024, 200, 20, 10, 24)])
+def test_peer_exchange_kernels_on_one_gpu(world, H, W, K, T, halo):
+    """smk_peer_push / smk_peer_unpack with every slab in this process (the "remote" mailboxes are the other slabs' tensors):
+    the mailbox addressing, the two-slot parity, the counters and the ghost-row offsets -- u's extra staggered row, v's wider
+    pitch -- against the undecomposed run, bit for bit, over enough steps for both slots to be reused several times."""
+    st0 = random_state(H, W, seed=33 + world)
+    grp = LocalGroup((H, W), 0.02, 0.01, "cuda", world=world, jacobi_iters=K, sweeps_per_launch=T, halo=halo, peer=True)
+    whole = NavierStokesSimulator((H, W), 0.02, 0.01, "cuda", jacobi_iters=K)
+    for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+        grp.scatter(k, st0[k])
+        setattr(whole, name, torch.from_numpy(st0[k]).cuda())
+    for _ in range(5):
+        grp.step()
+        whole.step()
+    grp.check()
+    for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+        ref = N(getattr(whole, name))
+        assert_same(N(grp.gather(k))[:, :ref.shape[1]], ref, "%s, peer kernels, world %d" % (k, world))
+    # the counters moved in lockstep: every slab completed the same number of exchanges
+    seqs = {int(s.exchanger.buf[-PeerSeqOffset:].view(torch.int32)[2].item()) for s in grp.slabs}
+    assert len(seqs) == 1 and seqs.pop() > 0
+
+
+def test_slab_step_in_one_c_call_equals_the_phase_calls():
+    """smk_slab_step (one C call per step) against the per-phase entry points on an undecomposed grid."""
+    H, W, K = 300, 260, 12
+    st0 = random_state(H, W, seed=8)
+    a = SlabNavierStokes((H, W), 0.02, 0.01, "cuda", rank=0, world=1, jacobi_iters=K, sweeps_per_launch=6)
+    b = NavierStokesSimulator((H, W), 0.02, 0.01, "cuda", jacobi_iters=K, sweeps_per_launch=6, step_kernel="phases")
+    for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+        a.scatter(k, st0[k])
+        setattr(b, name, torch.from_numpy(st0[k]).cuda())
+    n0 = _lib.launch_count()
+    for _ in range(3):
+        a.step()
+    assert _lib.launch_count() - n0 == 3 * (1 + 2 + 1 + 3)
+    for _ in range(3):
+        b.step()
+    for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+        ref = N(getattr(b, name))
+        assert_same(N(a.owned(k))[:, :ref.shape[1]], ref, k)
