@@ -89,7 +89,7 @@ def phase_flops_per_cell(K, sweeps_in_launch, steps_in_launch=1):
 
 KERNEL_NAMES = {"jacobi": "k_jacobi", "forces_diffuse_div": "k_forces_diffuse_div", "project": "k_project",
                 "advect_u": "k_advect(u)", "advect_v": "k_advect(v)", "advect_d": "k_advect(density)", "splat": "k_splat",
-                "project_advect_u": "k_project_advect_u", "step_fused": "k_step_fused", "other": "other", "halo": "k_halo_push + k_halo_unpack"}
+                "project_advect_u": "k_advect_tiled<1>(u) with k_project fused in", "step_fused": "k_step_fused", "other": "other", "halo": "k_halo_push + k_halo_unpack"}
 
 
 def emitters_for_sequence(s, h, w):
@@ -427,6 +427,8 @@ def kernel_rooflines(ctx, key, prof, K, T, steps, cells_per_launch, clk, fits_l2
         sweeps = K * T * steps / n if ph == "jacobi" else 0
         nsteps = T * steps / n if ph == "step_fused" else 1
         bpc, fpc = phase_bytes_per_cell(K, sweeps, nsteps)[ph], phase_flops_per_cell(K, sweeps, nsteps)[ph]
+        if ph == "advect_v" and prof.get("project_advect_u", (0, 0))[1]:
+            bpc, fpc = bpc + 4, fpc + 3                     # the v advection then re-reads p and projects v itself
         t = ms / n * 1e-3
         gbs, tfs = bpc * cells_per_launch / t / 1e9, fpc * cells_per_launch / t / 1e12
         traffic = committed_traffic(ph, key)

@@ -285,6 +285,11 @@ SMK_API int smk_peer_unpack(const smk_peer_comm_t* c, float* const* field_base_h
 SMK_API int smk_slab_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, const smk_peer_comm_t* comm,
                           const smk_slab_check_t* chk_u, const smk_slab_check_t* chk_v, const smk_slab_check_t* chk_d, void* stream);
 
+/*     the tail of that step alone: gradient subtract (:148-149) + advection of u, v, density (:166-168) + decay (:171) on the live
+ *     copies, which flip.  On big fields the gradient subtract is fused into the u and v advections (SMK_PROJECT_FUSED=0 disables). */
+SMK_API int smk_project_advect(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
+                               const smk_slab_check_t* chk_u, const smk_slab_check_t* chk_v, const smk_slab_check_t* chk_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -165,6 +165,27 @@ static hx_range_fn hx_range()
 
 using namespace smk;
 
+#define SMK_TRY_(x) do { const int rc_ = (x); if (rc_ != SMK_OK) return rc_; } while (0)
+
+// The tail of a step on a (slab) grid whose live u, v, density are the outputs of forces + diffusion and whose live p holds the
+// K sweeps: gradient subtract (navier_stokes.py:148-149), sequential advection of u, v, density (:166-168), decay (:171).
+// The live copies flip (u, v, density end up in the other copy).  On big fields the gradient subtract runs inside the u and v
+// advections (k_advect_tiled<.., 1 / 2>, stencil.cu); else k_project runs on its own first.
+static int project_advect(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
+                          const smk_slab_check_t* chk_u, const smk_slab_check_t* chk_v, const smk_slab_check_t* chk_d, cudaStream_t s)
+{
+    const int cu = st->cur_u, cv = st->cur_v, cd = st->cur_d;
+    float *u1 = st->u[cu], *u0 = st->u[cu ^ 1], *v1 = st->v[cv], *v0 = st->v[cv ^ 1], *d1 = st->d[cd], *d0 = st->d[cd ^ 1];
+    const float* pl = st->p[st->cur_p];
+    const bool fuse = advect_can_fuse_project(g);
+    if (!fuse) SMK_TRY_(launch_project(g, pl, u1, v1, prm->dt, s));
+    SMK_TRY_(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, 0, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, chk_u, s, fuse ? 1 : 0, pl));
+    SMK_TRY_(launch_advect(g, v1, v0, g->h, g->w + 1, g->pitch_v, 0, u0, v1, prm->dt, 1.0f, nullptr, 0, nullptr, chk_v, s, fuse ? 2 : 0, pl));
+    SMK_TRY_(launch_advect(g, d1, d0, g->h, g->w, g->pitch_c, 0, u0, v0, prm->dt, prm->decay, nullptr, 0, nullptr, chk_d, s));
+    st->cur_u = cu ^ 1; st->cur_v = cv ^ 1; st->cur_d = cd ^ 1;
+    return SMK_OK;
+}
+
 #define SMK_TRY(x) do { const int rc_ = (x); if (rc_ != SMK_OK) return rc_; } while (0)
 
 extern "C" {
@@ -246,19 +267,31 @@ int smk_slab_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
         SMK_TRY(peer_xfer(comm, base, false, s));
     }
     const int cu = st->cur_u, cv = st->cur_v, cd = st->cur_d;
-    float *u0 = st->u[cu], *u1 = st->u[cu ^ 1], *v0 = st->v[cv], *v1 = st->v[cv ^ 1], *d0 = st->d[cd], *d1 = st->d[cd ^ 1];
     // 1-2. buoyancy + diffusion + divergence                                   navier_stokes.py:154-160, :136
-    SMK_TRY(launch_forces_diffuse_div(g, u0, v0, d0, u1, v1, d1, st->div, prm->dt, prm->c_uv, prm->c_d, s));
-    // 3. Jacobi sweeps + gradient subtract                                     :139-149
+    SMK_TRY(launch_forces_diffuse_div(g, st->u[cu], st->v[cv], st->d[cd], st->u[cu ^ 1], st->v[cv ^ 1], st->d[cd ^ 1], st->div,
+                                      prm->dt, prm->c_uv, prm->c_d, s));
+    st->cur_u = cu ^ 1; st->cur_v = cv ^ 1; st->cur_d = cd ^ 1;
+    // 3. Jacobi sweeps                                                         :139-145
     int flip = 0;
     SMK_TRY(launch_jacobi(g, st->div, st->p[st->cur_p], st->p[st->cur_p ^ 1], prm->jacobi_iters, prm->sweeps_per_launch, &flip, s));
     st->cur_p ^= flip;
-    SMK_TRY(launch_project(g, st->p[st->cur_p], u1, v1, prm->dt, s));
-    // 4. sequential advection (:166-168), 5. decay (:171).  u, v, density end up in the copies they started in.
-    SMK_TRY(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, 0, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, chk_u, s));
-    SMK_TRY(launch_advect(g, v1, v0, g->h, g->w + 1, g->pitch_v, 0, u0, v1, prm->dt, 1.0f, nullptr, 0, nullptr, chk_v, s));
-    SMK_TRY(launch_advect(g, d1, d0, g->h, g->w, g->pitch_c, 0, u0, v0, prm->dt, prm->decay, nullptr, 0, nullptr, chk_d, s));
-    return SMK_OK;
+    // 4-5. gradient subtract + the three advections + decay                    :148-149, :166-171
+    return project_advect(g, st, prm, chk_u, chk_v, chk_d, s);
+}
+
+int smk_project_advect(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
+                       const smk_slab_check_t* chk_u, const smk_slab_check_t* chk_v, const smk_slab_check_t* chk_d, void* stream)
+{
+    SMK_TRY(check_grid(g, "smk_project_advect"));
+    if (!st || !prm) return fail(SMK_EINVAL, "smk_project_advect: state/params NULL");
+    if (g->batch != 1) return fail(SMK_EUNSUPPORTED, "smk_project_advect: batch must be 1");
+    const void* ps[] = {st->u[0], st->u[1], st->v[0], st->v[1], st->d[0], st->d[1], st->p[0], st->p[1]};
+    for (const void* p : ps)
+        if (!p || !aligned16(p)) return fail(SMK_EINVAL, "smk_project_advect: a state pointer is NULL or not 16-byte aligned");
+    if ((st->cur_u | st->cur_v | st->cur_d | st->cur_p) & ~1) return fail(SMK_EINVAL, "smk_project_advect: cur_* must be 0 or 1");
+    for (const smk_slab_check_t* c : {chk_u, chk_v, chk_d})
+        if (c && (!c->overflow_flag || c->need_lo > c->need_hi || c->valid_lo > c->valid_hi)) return fail(SMK_EINVAL, "smk_project_advect: bad check ranges");
+    return project_advect(g, st, prm, chk_u, chk_v, chk_d, (cudaStream_t)stream);
 }
 
 }  // extern "C"

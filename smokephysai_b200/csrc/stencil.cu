@@ -3,6 +3,7 @@
 // stencils or gathers: coalesced row-major access, shared-memory staging with halos where a phase reuses
 // neighbours, no tensor cores (nothing here is a contraction).
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 
 namespace smk {
@@ -380,6 +381,7 @@ struct AdvectArgs {
     unsigned ngroups; unsigned long long magic;          // row = (idx * magic) >> 40 == idx / ngroups (+ fix-up)
     int row0, gh;                                        // slab: global row of local row 0, global cell rows
     int need_lo, need_hi, valid_lo, valid_hi; int* overflow;
+    const float* P; int pc; long long sc_;               // k_advect_tiled<.., PROJ>: pressure for the fused gradient subtract
 };
 
 template <bool SLAB>
@@ -493,15 +495,39 @@ struct AdvectTile {
     float sV[AT_R + 1][AT_VP];
 };
 
+// ... with the gradient subtract (a7, navier_stokes.py:148-149) fused in: the pressure window behind the staged field window
+// (one more row above for u's p[i-1][j], one more column to the left for v's p[i][j-1]; 16-byte aligned columns)
+constexpr int AT_PR = AT_FR + 1, AT_PP = AT_FP + 8;                    // 25 rows x 144 columns: rows [i0-5, i0+20), columns [j0-8, j0+136)
+struct AdvectTileP {
+    AdvectTile t;
+    float sP[AT_PR][AT_PP];
+};
+
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ float2 neg2(const float2 a) { return make_float2(-a.x, -a.y); }
 
-template <bool SLAB, bool INTERIOR>
-__device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, const float* F, const float* U, const float* V, float* O,
-                                            const size_t b, const int i0, const int j0)
+// One value of the advected field straight from global memory (the rare back-trace that leaves the staged window), with the
+// gradient subtract applied on the fly when the kernel fuses it (PROJ 1: the field is u, 2: the field is v).
+template <int PROJ>
+__device__ __forceinline__ float advect_global(const AdvectArgs& a, const float* F, const float* P, const int y, const int x)
+{
+    float f = __ldg(F + ((unsigned)y * a.pitch + x));
+    if (PROJ == 1 && y >= 1 && y <= a.h - 1 && x < a.w) f = f - a.dt * (__ldg(P + ((unsigned)y * a.pc + x)) - __ldg(P + ((unsigned)(y - 1) * a.pc + x)));
+    if (PROJ == 2 && x >= 1 && x <= a.w - 1 && y < a.h) f = f - a.dt * (__ldg(P + ((unsigned)y * a.pc + x)) - __ldg(P + ((unsigned)y * a.pc + x - 1)));
+    return f;
+}
+
+// PROJ: 0 plain advection; 1 / 2: k_project fused in -- the staged u (1: the field window and the u tile) and v (1 and 2: the
+// v tile; 2: the field window) are the UNPROJECTED arrays and get u -= dt (p[i][j] - p[i-1][j]), v -= dt (p[i][j] - p[i][j-1])
+// in shared memory, from a pressure window staged next to them, before the advection reads them.  Same two rounded operations
+// per cell as k_project, so the result is bit-identical to project-then-advect; the projected u is never written to memory
+// (only the u advection reads it) and the projected v is recomputed by the v advection (PROJ 2) instead of being written.
+template <bool SLAB, bool INTERIOR, int PROJ>
+__device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, float (*sP)[AT_PP], const float* F, const float* U, const float* V,
+                                            const float* P, float* O, const size_t b, const int i0, const int j0)
 {
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const int w = a.w, rows = a.rows, cols = a.cols, pitch = a.pitch;
@@ -536,9 +562,48 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
             if (INTERIOR || j0 + 4 * lane < a.pv) cp_async16(&T.sV[r][4 * lane], V + ((unsigned)y * a.pv + j0 + 4 * lane));
         }
     }
+    if (PROJ) {
+        // pressure window rows [i0-5, i0+20) x columns [j0-8, j0+136): 25 rows of 36 16-byte chunks
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = wp + 8 * rr, y = i0 - AT_HB - 1 + r;
+            if (r < AT_PR && (INTERIOR || (y >= 0 && y < a.h))) {
+                const int x = j0 - 8 + 4 * lane;
+                const int off = y * a.pc + x;
+                if (INTERIOR || (x >= 0 && x < a.pc)) cp_async16(&sP[r][4 * lane], P + off);
+                if (lane < 4 && (INTERIOR || (x + 128 >= 0 && x + 128 < a.pc))) cp_async16(&sP[r][128 + 4 * lane], P + (off + 128));
+            }
+        }
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    if (PROJ) {
+        const float dt = a.dt;
+        // field window: row r <-> y = i0 - 4 + r <-> sP row r + 1; column c <-> x = j0 - 4 + c <-> sP column c + 4
+        for (int k = tid; k < AT_FR * AT_FP; k += 256) {
+            const int r = k / AT_FP, c = k - r * AT_FP, y = i0 - AT_HB + r, x = j0 - AT_HB + c;
+            if (PROJ == 1) {
+                if (INTERIOR || (y >= 1 && y <= a.h - 1 && x >= 0 && x < w))
+                    T.sF[r][c] = T.sF[r][c] - dt * (sP[r + 1][c + 4] - sP[r][c + 4]);
+            } else {
+                if (INTERIOR || (y >= 0 && y < a.h && x >= 1 && x <= w - 1))
+                    T.sF[r][c] = T.sF[r][c] - dt * (sP[r + 1][c + 4] - sP[r + 1][c + 3]);
+            }
+        }
+        if (PROJ == 1)                                   // u tile: row r <-> y = i0 + r <-> sP row r + 5; column c <-> x = j0 + c <-> sP column c + 8
+            for (int k = tid; k < AT_R * (AT_C + 1); k += 256) {
+                const int r = k / (AT_C + 1), c = k - r * (AT_C + 1), y = i0 + r, x = j0 + c;
+                if (INTERIOR || (y >= 1 && y <= a.h - 1 && x < w))
+                    T.sU[r][c] = T.sU[r][c] - dt * (sP[r + 5][c + 8] - sP[r + 4][c + 8]);
+            }
+        for (int k = tid; k < (AT_R + 1) * AT_C; k += 256) {     // v tile
+            const int r = k / AT_C, c = k - r * AT_C, y = i0 + r, x = j0 + c;
+            if (INTERIOR || (y < a.h && x >= 1 && x <= w - 1))
+                T.sV[r][c] = T.sV[r][c] - dt * (sP[r + 5][c + 8] - sP[r + 5][c + 7]);
+        }
+        __syncthreads();
+    }
 
     // slab: h is the GLOBAL cell-row count and gi the global row of this thread's cells; memory stays local
     const int h = SLAB ? a.gh : a.h;
@@ -601,11 +666,18 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
                     fy1.x = fminf(fy1.x, ymax); fy1.y = fminf(fy1.y, ymax);
                     const int dxa = (fx1.x != fx0.x) ? 1 : 0, dxb = (fx1.y != fx0.y) ? 1 : 0;
                     const int dya = (fy1.x != fy0.x) ? 1 : 0, dyb = (fy1.y != fy0.y) ? 1 : 0;
-                    const float* qa = F + ((unsigned)y0a * pitch + x0a);
-                    const float* qb = F + ((unsigned)y0b * pitch + x0b);
-                    const int oya = dya * pitch, oyb = dyb * pitch;
-                    f00 = make_float2(__ldg(qa), __ldg(qb)); f01 = make_float2(__ldg(qa + dxa), __ldg(qb + dxb));
-                    f10 = make_float2(__ldg(qa + oya), __ldg(qb + oyb)); f11 = make_float2(__ldg(qa + oya + dxa), __ldg(qb + oyb + dxb));
+                    if (PROJ) {
+                        f00 = make_float2(advect_global<PROJ>(a, F, P, y0a, x0a), advect_global<PROJ>(a, F, P, y0b, x0b));
+                        f01 = make_float2(advect_global<PROJ>(a, F, P, y0a, x0a + dxa), advect_global<PROJ>(a, F, P, y0b, x0b + dxb));
+                        f10 = make_float2(advect_global<PROJ>(a, F, P, y0a + dya, x0a), advect_global<PROJ>(a, F, P, y0b + dyb, x0b));
+                        f11 = make_float2(advect_global<PROJ>(a, F, P, y0a + dya, x0a + dxa), advect_global<PROJ>(a, F, P, y0b + dyb, x0b + dxb));
+                    } else {
+                        const float* qa = F + ((unsigned)y0a * pitch + x0a);
+                        const float* qb = F + ((unsigned)y0b * pitch + x0b);
+                        const int oya = dya * pitch, oyb = dyb * pitch;
+                        f00 = make_float2(__ldg(qa), __ldg(qb)); f01 = make_float2(__ldg(qa + dxa), __ldg(qb + dxb));
+                        f10 = make_float2(__ldg(qa + oya), __ldg(qb + oyb)); f11 = make_float2(__ldg(qa + oya + dxa), __ldg(qb + oyb + dxb));
+                    }
                 }
             } else {
                 fx1.x = fminf(fx1.x, xmax); fx1.y = fminf(fx1.y, xmax);
@@ -636,11 +708,18 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
                     f00 = make_float2(qa[0], qb[0]); f01 = make_float2(qa[dxa], qb[dxb]);
                     f10 = make_float2(qa[oya], qb[oyb]); f11 = make_float2(qa[oya + dxa], qb[oyb + dxb]);
                 } else {
-                    const float* qa = F + ((unsigned)y0a * pitch + x0a);
-                    const float* qb = F + ((unsigned)y0b * pitch + x0b);
-                    const int oya = dya * pitch, oyb = dyb * pitch;
-                    f00 = make_float2(__ldg(qa), __ldg(qb)); f01 = make_float2(__ldg(qa + dxa), __ldg(qb + dxb));
-                    f10 = make_float2(__ldg(qa + oya), __ldg(qb + oyb)); f11 = make_float2(__ldg(qa + oya + dxa), __ldg(qb + oyb + dxb));
+                    if (PROJ) {
+                        f00 = make_float2(advect_global<PROJ>(a, F, P, y0a, x0a), advect_global<PROJ>(a, F, P, y0b, x0b));
+                        f01 = make_float2(advect_global<PROJ>(a, F, P, y0a, x0a + dxa), advect_global<PROJ>(a, F, P, y0b, x0b + dxb));
+                        f10 = make_float2(advect_global<PROJ>(a, F, P, y0a + dya, x0a), advect_global<PROJ>(a, F, P, y0b + dyb, x0b));
+                        f11 = make_float2(advect_global<PROJ>(a, F, P, y0a + dya, x0a + dxa), advect_global<PROJ>(a, F, P, y0b + dyb, x0b + dxb));
+                    } else {
+                        const float* qa = F + ((unsigned)y0a * pitch + x0a);
+                        const float* qb = F + ((unsigned)y0b * pitch + x0b);
+                        const int oya = dya * pitch, oyb = dyb * pitch;
+                        f00 = make_float2(__ldg(qa), __ldg(qb)); f01 = make_float2(__ldg(qa + dxa), __ldg(qb + dxb));
+                        f10 = make_float2(__ldg(qa + oya), __ldg(qb + oyb)); f11 = make_float2(__ldg(qa + oya + dxa), __ldg(qb + oyb + dxb));
+                    }
                 }
             }
             const float2 ax = __fadd2_rn(fx1, neg2(px)), bx = __fadd2_rn(px, neg2(fx0));
@@ -687,17 +766,20 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
     }
 }
 
-template <bool SLAB>
-__global__ void __launch_bounds__(256, 6)        // 40 registers: 6 CTAs per SM beat 4 (62 registers) by 12 % and 7 (32, spills) by 5 %
+template <bool SLAB, int PROJ>
+__global__ void __launch_bounds__(256, PROJ ? 5 : 6)        // 40 registers: 6 CTAs per SM beat 4 (62 registers) by 12 % and 7 (32, spills) by 5 %; the pressure window of the fused variants leaves room for 5
 k_advect_tiled(const AdvectArgs a)
 {
     pdl_prologue();
-    __shared__ __align__(16) AdvectTile T;
+    __shared__ __align__(16) typename std::conditional<PROJ != 0, AdvectTileP, AdvectTile>::type TT;
+    AdvectTile& T = *reinterpret_cast<AdvectTile*>(&TT);
+    float (*sP)[AT_PP] = PROJ ? reinterpret_cast<float (*)[AT_PP]>(reinterpret_cast<char*>(&TT) + sizeof(AdvectTile)) : nullptr;
     const int i0 = blockIdx.y * AT_R, j0 = blockIdx.x * AT_C;
     const size_t b = blockIdx.z;
     const float* F = a.F + b * a.stride;
     const float* U = a.U + b * a.su_;
     const float* V = a.V + b * a.sv_;
+    const float* P = PROJ ? a.P + b * a.sc_ : nullptr;
     float* O = a.O + b * a.stride;
     asm volatile("" : "+l"(F));
     asm volatile("" : "+l"(U));
@@ -707,16 +789,31 @@ k_advect_tiled(const AdvectArgs a)
     // strictly before the last row / column of the (global) grid, so no sample is zeroed and nothing needs a bound
     const int gi_last = (SLAB ? a.row0 : 0) + i0 + AT_R - 1;
     const int h = SLAB ? a.gh : a.h;
-    const bool interior = i0 >= AT_HB && i0 + AT_R + AT_HB <= a.rows && j0 >= AT_HB && j0 + AT_C + AT_HB <= a.pitch &&
-                          j0 + AT_C + 4 <= a.pu && j0 + AT_C <= a.pv && i0 + AT_R + 1 <= a.h &&
-                          j0 + AT_C - 1 <= a.w - 2 && gi_last <= h - 2 && j0 + AT_C <= a.cols && j0 + AT_C <= a.frame_pitch;
-    if (interior) advect_tile<SLAB, true>(a, T, F, U, V, O, b, i0, j0);
-    else          advect_tile<SLAB, false>(a, T, F, U, V, O, b, i0, j0);
+    bool interior = i0 >= AT_HB && i0 + AT_R + AT_HB <= a.rows && j0 >= AT_HB && j0 + AT_C + AT_HB <= a.pitch &&
+                    j0 + AT_C + 4 <= a.pu && j0 + AT_C <= a.pv && i0 + AT_R + 1 <= a.h &&
+                    j0 + AT_C - 1 <= a.w - 2 && gi_last <= h - 2 && j0 + AT_C <= a.cols && j0 + AT_C <= a.frame_pitch;
+    // fused gradient subtract: the pressure window lies inside p, and every staged cell is one that k_project updates
+    // (u rows 1 .. h-1: the window starts at row i0 - 4 >= 1; v columns 1 .. w-1: the window starts at column j0 - 4 >= 1)
+    if (PROJ) interior = interior && i0 >= AT_HB + 1 && i0 + AT_R + AT_HB <= a.h && j0 >= 8 && j0 + AT_C + 8 <= a.pc && j0 + AT_C + AT_HB <= a.w;
+    if (interior) advect_tile<SLAB, true, PROJ>(a, T, sP, F, U, V, P, O, b, i0, j0);
+    else          advect_tile<SLAB, false, PROJ>(a, T, sP, F, U, V, P, O, b, i0, j0);
+}
+
+// proj / p: 0 / NULL for the plain advection; 1 (the field is u) or 2 (the field is v) fuses the gradient subtract of the pressure p
+// into the tiled kernel (u, v and the field are then the UNPROJECTED arrays).  advect_can_fuse_project() tells whether the launch
+// would take the tiled kernel; callers that get `false` run k_project first and pass proj = 0.
+bool advect_can_fuse_project(const smk_grid_t* g)
+{
+    if (env().project_fused == 0) return false;
+    const int tiled = env().advect_tiled != SMK_ENV_UNSET ? env().advect_tiled : -1;
+    const bool big = (int64_t)g->h * g->w * g->batch >= (int64_t)6 << 20;
+    const bool forced = env().project_fused == 1 && tiled != 0;
+    return (tiled == 1 || (tiled == -1 && big) || forced) && (g->h + 1 + AT_R - 1) / AT_R <= 65535;
 }
 
 int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows, int cols, int pitch, int64_t stride,
                   const float* u, const float* v, float dt, float scale, float* frame, int64_t frame_stride,
-                  const float* fmul, const smk_slab_check_t* chk, cudaStream_t s)
+                  const float* fmul, const smk_slab_check_t* chk, cudaStream_t s, int proj, const float* p)
 {
     if ((int64_t)rows * pitch >= (1ll << 31)) return fail(SMK_EUNSUPPORTED, "smk_advect: field of %d x %d exceeds 2^31 elements", rows, pitch);
     AdvectArgs a;
@@ -730,8 +827,18 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
     a.row0 = g->row0; a.gh = g->gh;
     a.need_lo = chk ? chk->need_lo : 0; a.need_hi = chk ? chk->need_hi : 0;
     a.valid_lo = chk ? chk->valid_lo : 0; a.valid_hi = chk ? chk->valid_hi : 0; a.overflow = chk ? chk->overflow_flag : nullptr;
+    a.P = p; a.pc = g->pitch_c; a.sc_ = g->stride_c;
     const unsigned long long nthreads = (unsigned long long)rows * a.ngroups;
     dim3 grid((unsigned)((nthreads + 255) / 256), g->batch);
+    if (proj) {
+        if (!p || (proj != 1 && proj != 2) || !advect_can_fuse_project(g)) return fail(SMK_EINVAL, "launch_advect: fused gradient subtract needs p and the tiled kernel");
+        ProfScope prof_(proj == 1 ? SMK_PH_PROJECT_ADVECT_U : SMK_PH_ADVECT_V, s);
+        dim3 tgrid((unsigned)((pitch + AT_C - 1) / AT_C), (unsigned)((rows + AT_R - 1) / AT_R), g->batch);
+        const bool slab_ = g->gh != 0 && (g->gh != g->h || g->row0 != 0);
+        if (proj == 1) { if (slab_) launch_chain(k_advect_tiled<true, 1>, tgrid, dim3(256), 0, s, a); else launch_chain(k_advect_tiled<false, 1>, tgrid, dim3(256), 0, s, a); }
+        else           { if (slab_) launch_chain(k_advect_tiled<true, 2>, tgrid, dim3(256), 0, s, a); else launch_chain(k_advect_tiled<false, 2>, tgrid, dim3(256), 0, s, a); }
+        return check_launch("k_advect_tiled (fused gradient subtract)");
+    }
     ProfScope prof_(rows == g->h + 1 ? SMK_PH_ADVECT_U : (cols == g->w + 1 ? SMK_PH_ADVECT_V : SMK_PH_ADVECT_D), s);
     // the tiled kernel wins on big fields (8192^2: 182 against 229 us), the direct one on small ones (1024^2: 10.0
     // against 10.7 us; equal at 2048^2): -1 picks by size, SMK_ADVECT_TILED = 0 / 1 forces one of them
@@ -740,8 +847,8 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
     const bool big = (int64_t)rows * cols * g->batch >= (int64_t)6 << 20;
     if ((tiled == 1 || (tiled == -1 && big)) && (rows + AT_R - 1) / AT_R <= 65535) {
         dim3 tgrid((unsigned)((pitch + AT_C - 1) / AT_C), (unsigned)((rows + AT_R - 1) / AT_R), g->batch);
-        if (slab) launch_chain(k_advect_tiled<true>, tgrid, dim3(256), 0, s, a);
-        else      launch_chain(k_advect_tiled<false>, tgrid, dim3(256), 0, s, a);
+        if (slab) launch_chain(k_advect_tiled<true, 0>, tgrid, dim3(256), 0, s, a);
+        else      launch_chain(k_advect_tiled<false, 0>, tgrid, dim3(256), 0, s, a);
         return check_launch("k_advect_tiled");
     }
     if (slab) launch_chain(k_advect<true>, grid, dim3(256), 0, s, a);

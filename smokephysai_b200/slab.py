@@ -261,28 +261,43 @@ class PeerExchanger:
         return base + 4 * (2 * self.region + k)
 
     def _wire_ipc(self):
+        """Export this rank's mailbox, map the neighbours'.  Collective: every rank goes through the same all_gather / all_reduce
+        whatever fails locally, and either every rank ends up wired or every rank raises SmokeLibraryError (so that a caller
+        can fall back to NCCL on all ranks together instead of leaving some of them waiting in a collective)."""
         import torch.distributed as dist
-        _lib.call("smk_set_device", self.device.index)     # the library's own CUDA runtime must be on this rank's device
-        handle = torch.zeros(72, dtype=torch.uint8)
-        off = C.c_int64(0)
-        _lib.call("smk_ipc_export", self.buf.data_ptr(), handle.data_ptr(), C.byref(off))
-        handle[64:72] = torch.frombuffer(bytearray(C.string_at(C.byref(off), 8)), dtype=torch.uint8)
         world = dist.get_world_size(self.group)
         on_gpu = dist.get_backend(self.group) == "nccl"
+        handle = torch.zeros(72, dtype=torch.uint8)
+        err = None
+        try:
+            _lib.call("smk_set_device", self.device.index)     # the library's own CUDA runtime must be on this rank's device
+            off = C.c_int64(0)
+            _lib.call("smk_ipc_export", self.buf.data_ptr(), handle.data_ptr(), C.byref(off))
+            handle[64:72] = torch.tensor(list(int(off.value).to_bytes(8, "little", signed=True)), dtype=torch.uint8)
+        except _lib.SmokeLibraryError as e:
+            err = e
         mine = handle.to(self.device) if on_gpu else handle
         every = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(every, mine, group=self.group)
         bases = {}
-        for peer in (self.geom.rank - 1, self.geom.rank + 1):
-            if 0 <= peer < world:
-                h = every[peer].cpu().contiguous()
-                poff = int.from_bytes(bytes(h[64:72].tolist()), "little", signed=True)
-                ptr = C.c_void_p()
-                _lib.call("smk_ipc_open", h.data_ptr(), poff, C.byref(ptr))
-                self._opened.append((ptr.value, poff))
-                bases[peer] = ptr.value
+        if err is None:
+            try:
+                for peer in (self.geom.rank - 1, self.geom.rank + 1):
+                    if 0 <= peer < world:
+                        h = every[peer].cpu().contiguous()
+                        poff = int.from_bytes(bytes(h[64:72].tolist()), "little", signed=True)
+                        ptr = C.c_void_p()
+                        _lib.call("smk_ipc_open", h.data_ptr(), poff, C.byref(ptr))
+                        self._opened.append((ptr.value, poff))
+                        bases[peer] = ptr.value
+            except _lib.SmokeLibraryError as e:
+                err = e
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.device if on_gpu else "cpu")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)     # also orders "every mapping exists" before the first push
+        if not int(ok.item()):
+            self.close()
+            raise _lib.SmokeLibraryError("peer halo exchange unavailable: %s" % (err if err is not None else "another rank could not map its neighbours"))
         self.wire(bases)
-        dist.barrier(group=self.group)                      # nobody pushes before every mapping exists
 
     def wire(self, bases):
         """bases: {neighbour rank: address of its mailbox tensor as seen from this process}."""
@@ -410,17 +425,10 @@ class SlabNavierStokes:
         if isinstance(self.exchanger, str) and self.exchanger == "peer":
             try:
                 self.exchanger = PeerExchanger(self.local._cuda, self.geom, self.local._layout)
-                ok = 1
-            except _lib.SmokeLibraryError:
+            except _lib.SmokeLibraryError:          # raised on every rank together (PeerExchanger._wire_ipc)
                 if exchange == "peer":
                     raise
-                ok = 0
-            if exchange == "auto":          # every rank must end up with the same kind of exchanger
-                import torch.distributed as dist
-                t = torch.tensor([ok], dtype=torch.int32, device=self.local._cuda)
-                dist.all_reduce(t, op=dist.ReduceOp.MIN)
-                if not int(t.item()):
-                    self.exchanger = NcclExchanger(self.local._cuda)
+                self.exchanger = NcclExchanger(self.local._cuda)
         self._overflow = torch.zeros(1, dtype=torch.int32, device=self.local._cuda)
         self.steps_done = 0
 
@@ -494,20 +502,12 @@ class SlabNavierStokes:
         return SlabCheck(g.own_lo, min(g.own_hi + 1, rows), lo, hi, self._overflow.data_ptr())
 
     def _project_advect(self):
+        """Gradient subtract + the three advections + decay in one C call (smk_project_advect: navier_stokes.py:148-149, :166-171)."""
         ns, g = self.local, self.geom
-        st, prm, L = ns._state, ns._params(), ns._layout
-        s = ns._stream()
-        _lib.call("smk_project", self._g(), st.p[st.cur_p], st.u[st.cur_u], st.v[st.cur_v], prm.dt, s)
-
-        def adv(k, rows, cols, pitch, scale):
-            arr, cur = getattr(st, k), getattr(st, "cur_" + k)
-            chk = self._check(rows)
-            _lib.call("smk_advect_slab", self._g(), arr[cur], arr[cur ^ 1], rows, cols, pitch, st.u[st.cur_u], st.v[st.cur_v],
-                      prm.dt, scale, C.byref(chk) if chk is not None else None, s)
-            setattr(st, "cur_" + k, cur ^ 1)
-        adv("u", g.hl + 1, g.W, L.pitch_u, 1.0)          # navier_stokes.py:166
-        adv("v", g.hl, g.W + 1, L.pitch_v, 1.0)          # :167 (uses the new u)
-        adv("d", g.hl, g.W, L.pitch_c, prm.decay)        # :168, :171
+        prm = ns._params()
+        chk = [self._check(rows) for rows in (g.hl + 1, g.hl, g.hl)]
+        ref = [C.byref(c) if c is not None else None for c in chk]
+        _lib.call("smk_project_advect", self._g(), C.byref(ns._state), C.byref(prm), ref[0], ref[1], ref[2], ns._stream())
         self.steps_done += 1
 
     def step_plan(self):
@@ -537,8 +537,11 @@ class SlabNavierStokes:
 
     def step(self):
         """One time step of this rank's slab (all ranks must call it together)."""
-        if self.world == 1 or (isinstance(self.exchanger, PeerExchanger) and self.single_exchange and self.exchanger.comm is not None
-                               and not getattr(self, "_phase_by_phase", False)):
+        if self.world == 1 or (self.single_exchange and self.exchanger and not getattr(self, "_phase_by_phase", False)):
+            # one exchange per step: the compute part is ONE C call (smk_slab_step), which also issues the exchange when it
+            # is the peer-store one; an NCCL / torch.distributed exchange is issued from here first
+            if self.world > 1 and not isinstance(self.exchanger, PeerExchanger):
+                self.exchange(("u", "v", "d", "p"))
             return self._c_step()
         for kind, arg in self.step_plan():
             if kind == "x":

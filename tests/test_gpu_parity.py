@@ -605,3 +605,28 @@ def test_simulator_on_another_device_leaves_the_current_device_alone():
     ref = SmokeSimulator((64, 64), device="cuda:0")
     ref.add_incense_source([(32, 32)], [1.0])
     assert_same(N(f), N(ref.simulate_step()), "cuda:1 vs cuda:0")
+
+
+@pytest.mark.parametrize("vel", [40.0, 600.0])
+@pytest.mark.parametrize("h,w", [(100, 400), (64, 300), (35, 260), (130, 1000), (48, 392), (300, 140), (129, 129)])
+def test_gradient_subtract_fused_into_the_tiled_advection_vs_oracle(h, w, vel):
+    """Big grids run k_project inside the u and v advections (k_advect_tiled<.., 1 / 2>: u, v projected in shared memory from
+    a staged pressure window).  SMK_PROJECT_FUSED=1 forces that path on small grids with interior AND edge tiles; vel = 600
+    makes back-traces of up to 12 cells, which leave the staged window and take the project-on-the-fly global path."""
+    rng = np.random.default_rng(h * 7 + w + int(vel))
+    ref = oracle.OracleSolver((h, w), 0.02, 0.01, 6)
+    ref.u = ((rng.random((h + 1, w)) - 0.5) * vel).astype(np.float32)
+    ref.v = ((rng.random((h, w + 1)) - 0.5) * vel).astype(np.float32)
+    ref.p = (rng.standard_normal((h, w)) * 50).astype(np.float32)
+    ref.density = rng.random((h, w)).astype(np.float32)
+    with smk_env(SMK_PROJECT_FUSED=1):
+        ns = make(h, w, 0.02, 0.01, 6, step_kernel="phases")
+        for k in ("u", "v", "p", "density"):
+            setattr(ns, k, T(getattr(ref, k)))
+        n0 = _lib.launch_count()
+        for t in range(2):
+            ref.step()
+            ns.step()
+            for k in ("u", "v", "p", "density"):
+                assert_same(N(getattr(ns, k)), getattr(ref, k), "%dx%d vel %g step %d %s" % (h, w, vel, t, k))
+        assert _lib.launch_count() - n0 == 2 * (1 + 1 + 3)          # no k_project launch: fdd, one Jacobi launch, three advections

@@ -102,7 +102,7 @@ def _nccl_worker(rank, world, port, H, W, K, T, steps, out_dir, exch):
     try:
         st0 = random_state(H, W, seed=21)
         from smokephysai_b200.slab import DistExchanger, NcclExchanger, PeerExchanger
-        halo = K + 4 if exch == "peer-one-call" else None
+        halo = K + 6 if exch == "peer-one-call" else None
         slab = SlabNavierStokes((H, W), 0.02, 0.01, "cuda:%d" % rank, rank=rank, world=world, jacobi_iters=K, sweeps_per_launch=T, halo=halo,
                                 exchanger=DistExchanger() if exch == "torch" else None,
                                 exchange="peer" if exch.startswith("peer") else "nccl")
@@ -176,8 +176,8 @@ def test_full_size_c4_slabs_equal_undecomposed():
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("world,H,W,K,T,halo", [(2, 200, 132, 8, 4, None), (3, 300, 260, 12, 6, 16), (4, 512, 384, 20, 10, None),
-                                                (8, 1024, 200, 20, 10, 24)])
+@pytest.mark.parametrize("world,H,W,K,T,halo", [(2, 200, 132, 8, 4, None), (3, 300, 260, 12, 6, 18), (4, 512, 384, 20, 10, None),
+                                                (8, 1024, 200, 20, 10, 26)])
 def test_peer_exchange_kernels_on_one_gpu(world, H, W, K, T, halo):
     """smk_peer_push / smk_peer_unpack with every slab in this process (the "remote" mailboxes are the other slabs' tensors):
     the mailbox addressing, the two-slot parity, the counters and the ghost-row offsets -- u's extra staggered row, v's wider
@@ -218,3 +218,27 @@ def test_slab_step_in_one_c_call_equals_the_phase_calls():
     for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
         ref = N(getattr(b, name))
         assert_same(N(a.owned(k))[:, :ref.shape[1]], ref, k)
+
+
+@pytest.mark.parametrize("world,H,W,K,T,halo", [(2, 200, 132, 8, 4, None), (3, 300, 260, 12, 6, 18), (4, 512, 384, 20, 10, 26)])
+def test_slabs_with_the_fused_gradient_subtract(world, H, W, K, T, halo):
+    """The slab step with k_project fused into the tiled u / v advections (forced on these small grids) against the undecomposed
+    run with k_project as its own kernel."""
+    from helpers import smk_env
+    st0 = random_state(H, W, seed=5 + world)
+    with smk_env(SMK_PROJECT_FUSED=0):
+        whole = NavierStokesSimulator((H, W), 0.02, 0.01, "cuda", jacobi_iters=K, step_kernel="phases")
+        for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+            setattr(whole, name, torch.from_numpy(st0[k]).cuda())
+        for _ in range(3):
+            whole.step()
+    with smk_env(SMK_PROJECT_FUSED=1):
+        grp = LocalGroup((H, W), 0.02, 0.01, "cuda", world=world, jacobi_iters=K, sweeps_per_launch=T, halo=halo)
+        for k in ("u", "v", "p", "d"):
+            grp.scatter(k, st0[k])
+        for _ in range(3):
+            grp.step()
+        grp.check()
+        for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+            ref = N(getattr(whole, name))
+            assert_same(N(grp.gather(k))[:, :ref.shape[1]], ref, "%s, fused gradient subtract in slabs, world %d" % (k, world))
