@@ -376,14 +376,22 @@ int smk_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, floa
     int flip = 0;
     SMK_TRY(launch_jacobi(g, st->div, st->p[st->cur_p], st->p[st->cur_p ^ 1], prm->jacobi_iters, prm->sweeps_per_launch, &flip, s));
     st->cur_p ^= flip;
-    // On big grids the gradient subtract is fused into the u and v advections (k_advect_tiled<.., 1 / 2>: u, v are projected in
-    // shared memory from a staged pressure window, 12 of 60 B per cell-step less traffic); else k_project runs on its own.
+    // On big grids the gradient subtract is fused into the u advection (k_advect_tiled<.., 1>: u, v are projected in shared memory
+    // from a staged pressure window; the projected u is never written, the projected v goes to the spare copy v0, and the v
+    // advection then runs v0 -> v1: the live v ends up in the other copy); else k_project runs on its own.
     const float* pl = st->p[st->cur_p];
     const bool fuse = advect_can_fuse_project(g);
-    if (!fuse) SMK_TRY(launch_project(g, pl, u1, v1, prm->dt, s));
     // 4. sequential advection: u, then v with the new u, then density with both :166-168; 5. decay :171; copy :173
-    SMK_TRY(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, g->stride_u, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, nullptr, s, fuse ? 1 : 0, pl));
-    SMK_TRY(launch_advect(g, v1, v0, g->h, g->w + 1, g->pitch_v, g->stride_v, u0, v1, prm->dt, 1.0f, nullptr, 0, nullptr, nullptr, s, fuse ? 2 : 0, pl));
+    if (fuse) {
+        SMK_TRY(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, g->stride_u, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, nullptr, s, 1, pl, v0));
+        SMK_TRY(launch_advect(g, v0, v1, g->h, g->w + 1, g->pitch_v, g->stride_v, u0, v0, prm->dt, 1.0f, nullptr, 0, nullptr, nullptr, s));
+        SMK_TRY(launch_advect(g, d1, d0, g->h, g->w, g->pitch_c, g->stride_c, u0, v1, prm->dt, prm->decay, frame, frame_stride, fmul, nullptr, s));
+        st->cur_v ^= 1;
+        return SMK_OK;
+    }
+    SMK_TRY(launch_project(g, pl, u1, v1, prm->dt, s));
+    SMK_TRY(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, g->stride_u, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, nullptr, s));
+    SMK_TRY(launch_advect(g, v1, v0, g->h, g->w + 1, g->pitch_v, g->stride_v, u0, v1, prm->dt, 1.0f, nullptr, 0, nullptr, nullptr, s));
     SMK_TRY(launch_advect(g, d1, d0, g->h, g->w, g->pitch_c, g->stride_c, u0, v0, prm->dt, prm->decay, frame, frame_stride, fmul, nullptr, s));
     return SMK_OK;
 }

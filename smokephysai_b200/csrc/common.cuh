@@ -123,7 +123,7 @@ int launch_project(const smk_grid_t* g, const float* p, float* u, float* v, floa
 int launch_bilerp(const float* f, int rows, int cols, int pitch, const float* y, const float* x, float* out, int64_t n, int mode, cudaStream_t s);
 int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows, int cols, int pitch, int64_t stride,
                   const float* u, const float* v, float dt, float scale, float* frame, int64_t frame_stride,
-                  const float* fmul, const smk_slab_check_t* chk, cudaStream_t s, int proj = 0, const float* p = nullptr);
+                  const float* fmul, const smk_slab_check_t* chk, cudaStream_t s, int proj = 0, const float* p = nullptr, float* vout = nullptr);
 bool advect_can_fuse_project(const smk_grid_t* g);
 int launch_div_norms(const smk_grid_t* g, const float* u, const float* v, float* out, cudaStream_t s);
 int launch_jacobi_residual(const smk_grid_t* g, const float* div, const float* p, float* out, cudaStream_t s);

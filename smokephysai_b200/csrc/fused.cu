@@ -129,29 +129,55 @@ __device__ __forceinline__ float4 zmask4(float4 v, const int c0, const int cols)
     return v;
 }
 
-// Four IEEE quotients n / d (navier_stokes.py:136 divides by dt).  nvcc's div.rn.f32 has a fast path (three FFMAs
-// around a reciprocal) and, for operands or quotients near the denormal range, a ~100-instruction subroutine; the
-// thin ring where the diffusing velocities underflow sends whole warps there every step.  Those warps take an
-// fp64 division instead: (float)((double)n / (double)d) is the correctly rounded fp32 quotient for every finite
-// n, d (53 >= 2*24 + 2 bits makes the double rounding innocuous, denormal results included: a quotient of two
-// 24-bit significands is either exactly a rounding midpoint or at least 2^-48 away from it in relative terms).
+// Four IEEE quotients n / d (navier_stokes.py:136 divides by dt).  nvcc's div.rn.f32 is, per quotient: MUFU.RCP of the divisor, two
+// FFMA that refine it to r1, then q0 = n * r1, rem = fma(q0, -d, n), q = fma(r1, rem, q0) -- guarded by FCHK and a branch to a
+// ~100-instruction subroutine for operands or quotients near the denormal range: 13 instructions and a reconvergence point per
+// quotient, 416 of the 612 instructions of the divergence phase.  The divisor is dt in every one of them, so FzDiv computes r1
+// ONCE per kernel with the very same three instructions and a quotient costs the three-instruction tail: bit-identical to
+// div.rn.f32's own fast path (it is that path).  Its validity range is enforced here instead of by FCHK:
+//   * |d| in [1e-6, 1e6] and d's significand not all ones (the one divisor class for which the tail can miss the rounding:
+//     Markstein's exception; checked on the CPU over all 2^31 numerators for r1 one ulp either side) -- else `fast` is false
+//     and every quotient takes the fp64 route below;
+//   * |n| in [1e-25, 1e25] or n == 0: quotient, remainder and products stay normal or exactly representable.  A warp that holds
+//     any other numerator (the thin ring where the diffusing velocities underflow) takes (float)((double)n / (double)d), the
+//     correctly rounded fp32 quotient for every finite n, d (53 >= 2*24 + 2 bits make the double rounding innocuous, denormal
+//     results included: a quotient of two 24-bit significands is either a rounding midpoint or at least 2^-48 away from one).
+struct FzDiv { float d, r1; bool fast; };
+__device__ __forceinline__ FzDiv zdiv_setup(const float d)
+{
+    FzDiv k;
+    k.d = d;
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d));
+    const float e = __fmaf_rn(r0, -d, 1.0f);
+    k.r1 = __fmaf_rn(r0, e, r0);
+    const float ad = fabsf(d);
+    k.fast = ad >= 1e-6f && ad <= 1e6f && (__float_as_uint(d) & 0x7fffffu) < 0x7ffffeu;
+    return k;
+}
 __device__ __forceinline__ bool zdiv_odd(const float x)
 {
     const float ax = fabsf(x);
-    return ax != 0.0f && !(ax >= 1e-30f && ax <= 1e30f);
+    return ax != 0.0f && !(ax >= 1e-25f && ax <= 1e25f);
 }
-__device__ __forceinline__ float4 zdiv4(float4 n, const float d)
+__device__ __forceinline__ float zdiv1(const float n, const FzDiv& k)
+{
+    const float q0 = __fmaf_rn(n, k.r1, 0.0f);
+    const float rem = __fmaf_rn(q0, -k.d, n);
+    return __fmaf_rn(k.r1, rem, q0);
+}
+__device__ __forceinline__ float4 zdiv4(float4 n, const FzDiv& k)
 {
 #ifdef SMK_PROBE_NODIV               // tools/micro only: what the step costs without the division (wrong results)
-    n.x *= d; n.y *= d; n.z *= d; n.w *= d;
+    n.x *= k.d; n.y *= k.d; n.z *= k.d; n.w *= k.d;
     return n;
 #endif
-    if (__any_sync(0xffffffffu, zdiv_odd(n.x) || zdiv_odd(n.y) || zdiv_odd(n.z) || zdiv_odd(n.w))) {
-        const double dd = (double)d;
+    if (!k.fast || __any_sync(0xffffffffu, zdiv_odd(n.x) || zdiv_odd(n.y) || zdiv_odd(n.z) || zdiv_odd(n.w))) {
+        const double dd = (double)k.d;
         n.x = (float)((double)n.x / dd); n.y = (float)((double)n.y / dd);
         n.z = (float)((double)n.z / dd); n.w = (float)((double)n.w / dd);
     } else {
-        n.x = n.x / d; n.y = n.y / d; n.z = n.z / d; n.w = n.w / d;
+        n.x = zdiv1(n.x, k); n.y = zdiv1(n.y, k); n.z = zdiv1(n.z, k); n.w = zdiv1(n.w, k);
     }
     return n;
 }
@@ -279,6 +305,7 @@ k_step_fused(const FusedArgs a)
     const bool xu = (h == 128) && lane < 8 && xe < w;
     const bool xv = (w == 128) && lane < 8 && xe < h;
     const float dt = a.dt;
+    const FzDiv fzdiv = zdiv_setup(dt);
 #ifdef SMK_FUSED_TIMING
     long long tick0_ = clock64();
 #endif
@@ -420,7 +447,7 @@ k_step_fused(const FusedArgs a)
                 o.y = ((ub.y - ua.y) + va.z) - va.y;
                 o.z = ((ub.z - ua.z) + va.w) - va.z;
                 o.w = ((ub.w - ua.w) + vr) - va.w;
-                o = zdiv4(o, dt);
+                o = zdiv4(o, fzdiv);
                 if (!FULL) {
                     if (i >= h) o = zero4;
                     if (c0 + 0 >= w) o.x = 0.f;
@@ -608,6 +635,458 @@ k_step_fused(const FusedArgs a)
     FZ_TICK(7);
 }
 
+// =====================================================================================================================
+// k_step_cluster<NC> -- ONE 128 x 128 simulation on a cluster of NC (2 or 4) CTAs, i.e. on NC SMs.
+//
+// k_step_fused gives a simulation one SM: with fewer simulations than SMs (BASELINE config 2 strong-scaled over 8 GPUs is 32
+// per GPU; a single interactive simulation is 1) most of the chip idles and a step takes the 41 us one SM needs.  Here the rows
+// are split over the CTAs of a thread-block cluster: CTA c owns rows [c RB, (c+1) RB), RB = 128 / NC, keeps them -- plus CH
+// halo rows on either side -- in its shared memory and its part of the pressure in registers, exactly as k_step_fused does for
+// the whole grid (same strip / cyclic mappings, same per-cell arithmetic: results are bit-identical).  What crosses CTAs goes
+// through distributed shared memory:
+//   * after a phase has rewritten a field, a CTA stores its first / last CH rows into the neighbours' halo rows (generic
+//     stores through cluster.map_shared_rank) and the cluster barrier publishes them;
+//   * a Jacobi sweep computes its boundary rows first, stores them into the neighbouring warps' (shared memory) and CTAs'
+//     (DSMEM) halo lines, ARRIVES on the cluster barrier, computes the interior rows, then WAITS: the ~380-cycle barrier
+//     latency hides under the interior arithmetic, and the barrier doubles as the CTA barrier of the sweep;
+//   * an advection back-trace that leaves the stored rows (more than about CH cells) gathers from the owner CTA's shared
+//     memory directly (ld through map_shared_rank); a cluster barrier separates everybody's gathers from the write-back.
+// Fields are addressed by GLOBAL row through "virtual" base pointers (storage base minus the first stored row), so the cell
+// code is k_step_fused's with r0 = c RB + 8 warp.
+// =====================================================================================================================
+constexpr int CH = 2;                                   // halo rows kept on either side of a CTA's band
+
+template <int NC> struct ClusterCfg {
+    static constexpr int RB = 128 / NC, NW = RB / 8, NT = NW * 32;
+    static constexpr int SU_ROWS = RB + 2 * CH + 1, SV_ROWS = RB + 2 * CH, SD_ROWS = RB + 2 * CH;
+    static constexpr int SU = SU_ROWS * FZ_PU, SV = SV_ROWS * FZ_PV, SD = SD_ROWS * FZ_PD;       // floats
+    static constexpr size_t SMEM = (size_t)(SU + SV + SD) * 4 + sizeof(float4) * (2 * 2 * NW * 32 + 2 * 2 * 32);
+};
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
+__device__ __forceinline__ unsigned cluster_rank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// the same shared-memory location in CTA `rank` of this cluster, as a generic pointer
+template <class T>
+__device__ __forceinline__ T* cluster_map(T* local, const unsigned rank)
+{
+    unsigned long long out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(reinterpret_cast<unsigned long long>(local)), "r"(rank));
+    return reinterpret_cast<T*>(out);
+}
+
+// a field of the cluster kernel: virtual bases (index by GLOBAL row) of this CTA's copy and of the two neighbours' copies
+struct CField {
+    float* mine; float* up; float* dn;       // up / dn are NULL at the ends of the cluster
+    int first, last;                          // global rows [first, last] this CTA owns
+};
+// store one float4 / float of an owned row, and into the neighbours' halo rows when the row is one they keep
+template <int PITCH>
+__device__ __forceinline__ void cput4(const CField& f, const int g, const int x, const float4 v)
+{
+    zsts4(f.mine + g * PITCH + x, v);
+    if (f.up && g < f.first + CH) zsts4(f.up + g * PITCH + x, v);
+    if (f.dn && g > f.last - CH) zsts4(f.dn + g * PITCH + x, v);
+}
+template <int PITCH>
+__device__ __forceinline__ void cput1(const CField& f, const int g, const int x, const float v)
+{
+    f.mine[g * PITCH + x] = v;
+    if (f.up && g < f.first + CH) f.up[g * PITCH + x] = v;
+    if (f.dn && g > f.last - CH) f.dn[g * PITCH + x] = v;
+}
+
+// zadvect_pair (above) for a CTA that stores rows [slo, shi] of the advected field: same operations in the same order;
+// a pair whose four corner rows are not all stored gathers from the owner CTAs through `far`.
+template <int PITCH, bool SCALE, int NC, class Far>
+__device__ __forceinline__ float2 cadvect_pair(const float* F, const int rows, const int cols, const float* su, const float* sv,
+                                               const int i, const int j, const float dt, const float scale,
+                                               const float slo, const float shi, const Far& far)
+{
+    constexpr int h = 128, w = 128;
+    const int j1 = j + 32;
+    const bool cu0 = (j <= w - 2 && i <= h - 1), cu1 = (j1 <= w - 2 && i <= h - 1);
+    const bool cv0 = (i <= h - 2 && j <= w - 1), cv1 = (i <= h - 2 && j1 <= w - 1);
+    const float2 ua = make_float2(cu0 ? su[i * FZ_PU + j] : 0.f, cu1 ? su[i * FZ_PU + j1] : 0.f);
+    const float2 ub = make_float2(cu0 ? su[i * FZ_PU + j + 1] : 0.f, cu1 ? su[i * FZ_PU + j1 + 1] : 0.f);
+    const float2 va = make_float2(cv0 ? sv[i * FZ_PV + j] : 0.f, cv1 ? sv[i * FZ_PV + j1] : 0.f);
+    const float2 vb = make_float2(cv0 ? sv[(i + 1) * FZ_PV + j] : 0.f, cv1 ? sv[(i + 1) * FZ_PV + j1] : 0.f);
+    const float2 half2 = make_float2(0.5f, 0.5f), dt2 = make_float2(dt, dt), one2 = make_float2(1.0f, 1.0f);
+    const float2 hua = __fmul2_rn(half2, ua), hub = __fmul2_rn(half2, ub);
+    const float2 hva = __fmul2_rn(half2, va), hvb = __fmul2_rn(half2, vb);
+    const float2 ui = make_float2(hua.x + hub.x, hua.y + hub.y);
+    const float2 vi = make_float2(hva.x + hvb.x, hva.y + hvb.y);
+    const float xmax = (float)(cols - 1), ymax = (float)(rows - 1);
+    const float2 du = __fmul2_rn(dt2, ui), dv = __fmul2_rn(dt2, vi);
+    float2 px = make_float2((float)j - du.x, (float)j1 - du.y);
+    float2 py = make_float2((float)i - dv.x, (float)i - dv.y);
+    px.x = fminf(fmaxf(px.x, 0.0f), xmax); px.y = fminf(fmaxf(px.y, 0.0f), xmax);
+    py.x = fminf(fmaxf(py.x, 0.0f), ymax); py.y = fminf(fmaxf(py.y, 0.0f), ymax);
+    const float2 fx0 = make_float2(floorf(px.x), floorf(px.y)), fy0 = make_float2(floorf(py.x), floorf(py.y));
+    float2 fx1 = __fadd2_rn(fx0, one2), fy1 = __fadd2_rn(fy0, one2);
+    fx1.x = fminf(fx1.x, xmax); fx1.y = fminf(fx1.y, xmax);
+    fy1.x = fminf(fy1.x, ymax); fy1.y = fminf(fy1.y, ymax);
+    const float2 ax = __fadd2_rn(fx1, zneg2(px)), bx = __fadd2_rn(px, zneg2(fx0));
+    const float2 ay = __fadd2_rn(fy1, zneg2(py)), by = __fadd2_rn(py, zneg2(fy0));
+    const int dx0 = (fx1.x != fx0.x) ? 1 : 0, dy0 = (fy1.x != fy0.x) ? 1 : 0;
+    const int dx1 = (fx1.y != fx0.y) ? 1 : 0, dy1 = (fy1.y != fy0.y) ? 1 : 0;
+    float2 f00, f01, f10, f11;
+    if (fy0.x >= slo && fy1.x <= shi && fy0.y >= slo && fy1.y <= shi) {
+        const float* q0 = F + (int)__fmaf_rn(fy0.x, (float)PITCH, fx0.x);
+        const float* q1 = F + (int)__fmaf_rn(fy0.y, (float)PITCH, fx0.y);
+        f00 = make_float2(q0[0], q1[0]); f01 = make_float2(q0[dx0], q1[dx1]);
+        f10 = make_float2(q0[dy0 * PITCH], q1[dy1 * PITCH]); f11 = make_float2(q0[dy0 * PITCH + dx0], q1[dy1 * PITCH + dx1]);
+    } else {
+        const int ya = (int)fy0.x, xa = (int)fx0.x, yb = (int)fy0.y, xb = (int)fx0.y;
+        f00 = make_float2(far(ya, xa), far(yb, xb)); f01 = make_float2(far(ya, xa + dx0), far(yb, xb + dx1));
+        f10 = make_float2(far(ya + dy0, xa), far(yb + dy1, xb)); f11 = make_float2(far(ya + dy0, xa + dx0), far(yb + dy1, xb + dx1));
+    }
+    const float2 t00 = __fmul2_rn(__fmul2_rn(ax, ay), f00), t01 = __fmul2_rn(__fmul2_rn(bx, ay), f01);
+    const float2 t10 = __fmul2_rn(__fmul2_rn(ax, by), f10), t11 = __fmul2_rn(__fmul2_rn(bx, by), f11);
+    float2 s = make_float2(t00.x + t01.x, t00.y + t01.y);
+    s.x = s.x + t10.x; s.y = s.y + t10.y;
+    s.x = s.x + t11.x; s.y = s.y + t11.y;
+    if (SCALE) s = __fmul2_rn(s, make_float2(scale, scale));
+    return s;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(ClusterCfg<NC>::NT, 1)
+k_step_cluster(const FusedArgs a)
+{
+    typedef ClusterCfg<NC> C;
+    constexpr int RB = C::RB, NW = C::NW, NT = C::NT;
+    constexpr int h = 128, w = 128, pu = 128, pv = 132, pc = 128;
+    extern __shared__ __align__(16) float smem[];
+    float* su_s = smem;                       // storage: row 0 of each array is global row g0 = c RB - CH
+    float* sv_s = su_s + C::SU;
+    float* sd_s = sv_s + C::SV;
+    float4 (*halo)[2][NW][32] = reinterpret_cast<float4 (*)[2][NW][32]>(sd_s + C::SD);
+    float4 (*xp)[2][32] = reinterpret_cast<float4 (*)[2][32]>(reinterpret_cast<float4*>(sd_s + C::SD) + 2 * 2 * NW * 32);   // [parity][0: from above, 1: from below]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = (int)cluster_rank();
+    const size_t b = blockIdx.x / NC;
+    const int g0 = c * RB - CH;               // first stored row (may be negative: rows outside the grid are never touched)
+    const int r0 = c * RB + warp * FZ_R, c0 = lane * 4;
+    const bool last_cta = c == NC - 1;
+    float* __restrict__ gU = a.U + b * a.su_;
+    float* __restrict__ gV = a.V + b * a.sv_;
+    float* __restrict__ gD = a.D + b * a.sc_;
+    float* __restrict__ gP = a.P + b * a.sc_;
+    const float dt = a.dt;
+    const FzDiv fzdiv = zdiv_setup(dt);
+
+    CField fu, fv, fd;
+    fu.mine = su_s - g0 * FZ_PU; fv.mine = sv_s - g0 * FZ_PV; fd.mine = sd_s - g0 * FZ_PD;
+    fu.up = fv.up = fd.up = fu.dn = fv.dn = fd.dn = nullptr;
+    if (c > 0) {
+        const int gn = (c - 1) * RB - CH;
+        fu.up = cluster_map(su_s, c - 1) - gn * FZ_PU; fv.up = cluster_map(sv_s, c - 1) - gn * FZ_PV; fd.up = cluster_map(sd_s, c - 1) - gn * FZ_PD;
+    }
+    if (!last_cta) {
+        const int gn = (c + 1) * RB - CH;
+        fu.dn = cluster_map(su_s, c + 1) - gn * FZ_PU; fv.dn = cluster_map(sv_s, c + 1) - gn * FZ_PV; fd.dn = cluster_map(sd_s, c + 1) - gn * FZ_PD;
+    }
+    fu.first = fv.first = fd.first = c * RB;
+    fv.last = fd.last = c * RB + RB - 1;
+    fu.last = last_cta ? 128 : c * RB + RB - 1;
+    float* const su = fu.mine; float* const sv = fv.mine; float* const sd = fd.mine;
+    float4 (*xp_up)[2][32] = c > 0 ? cluster_map(xp, c - 1) : nullptr;
+    float4 (*xp_dn)[2][32] = !last_cta ? cluster_map(xp, c + 1) : nullptr;
+    // rows of the stored windows that exist in the grid
+    const int slo = max(g0, 0);
+    const int shi_u = min(g0 + C::SU_ROWS - 1, 128), shi_c = min(g0 + C::SV_ROWS - 1, 127);
+    // u's staggered row 128 is owned by the last CTA: its 128 columns are spread over the lanes of that CTA
+    constexpr int XL = 128 / NW;              // lanes per warp that carry one extra cell
+    const int xe = XL * warp + lane;
+    const bool xu = last_cta && lane < XL;
+    // v's staggered column 128: one cell per owned row, lanes 0..7 of the warp that owns the row
+    const bool xv = lane < 8;
+    const int xr = r0 + lane;
+
+    // ---- load: stored rows of u, v, density (own rows and the halo rows, all straight from global memory), own pressure rows
+    for (int k = tid; k < (shi_u - slo + 1) * (pu / 4); k += NT) {
+        const int i = slo + k / (pu / 4), g = k % (pu / 4);
+        zsts4(su + i * FZ_PU + 4 * g, __ldcg(reinterpret_cast<const float4*>(gU + (size_t)i * pu + 4 * g)));
+    }
+    for (int k = tid; k < (shi_c - slo + 1) * (pv / 4); k += NT) {
+        const int i = slo + k / (pv / 4), g = k % (pv / 4);
+        zsts4(sv + i * FZ_PV + 4 * g, __ldcg(reinterpret_cast<const float4*>(gV + (size_t)i * pv + 4 * g)));
+    }
+    for (int k = tid; k < (shi_c - slo + 1) * (pc / 4); k += NT) {
+        const int i = slo + k / (pc / 4), g = k % (pc / 4);
+        zsts4(sd + i * FZ_PD + 4 * g, __ldcg(reinterpret_cast<const float4*>(gD + (size_t)i * pc + 4 * g)));
+    }
+    FzStrip P = {};
+    unsigned ringmask = 0;
+#pragma unroll
+    for (int r = 0; r < FZ_R; ++r) {
+        const int i = r0 + r;
+        packed_set_row(P, r, __ldcg(reinterpret_cast<const float4*>(gP + (size_t)i * pc + c0)));
+        if (i < 1 || i > h - 2) ringmask |= 1u << r;
+    }
+    FzElem M[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const float m = (c0 + cc >= 1 && c0 + cc <= w - 2) ? 0.25f : 0.f;
+        M[cc] = pe_make<FzElem>(make_float2(m, m));
+    }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+
+    // buoyancy (:154-155) on the owned rows of v and, redundantly, on the stored halo rows (they stay current without an exchange);
+    // the frame of the step just finished comes from the owned rows of density
+    auto frame_and_buoyancy = [&](float* frame, const bool buoy, const float4 (&mrow)[FZ_R]) {
+#pragma unroll
+        for (int r = 0; r < FZ_R; ++r) {
+            const int i = r0 + r;
+            const float4 d4 = zlds4(sd + i * FZ_PD + c0);
+            if (frame) {
+                float4 fr = d4;
+                if (a.fmul) {
+                    const float4 m = mrow[r];
+                    fr.x = fr.x + m.x * fr.x; fr.y = fr.y + m.y * fr.y; fr.z = fr.z + m.z * fr.z; fr.w = fr.w + m.w * fr.w;
+                }
+                *reinterpret_cast<float4*>(frame + (size_t)i * pc + c0) = fr;
+            }
+            if (buoy) {
+                float4 v4 = zlds4(sv + i * FZ_PV + c0);
+                v4.x = v4.x + dt * (d4.x * 0.1f); v4.y = v4.y + dt * (d4.y * 0.1f);
+                v4.z = v4.z + dt * (d4.z * 0.1f); v4.w = v4.w + dt * (d4.w * 0.1f);
+                zsts4(sv + i * FZ_PV + c0, v4);
+            }
+        }
+        if (buoy && tid < 2 * CH * 32) {                                 // the 2 CH halo rows: one float4 per thread
+            const int hr = tid >> 5;
+            const int i = hr < CH ? c * RB - CH + hr : c * RB + RB + (hr - CH);
+            if (i >= 0 && i <= h - 1) {
+                const float4 d4 = zlds4(sd + i * FZ_PD + c0);
+                float4 v4 = zlds4(sv + i * FZ_PV + c0);
+                v4.x = v4.x + dt * (d4.x * 0.1f); v4.y = v4.y + dt * (d4.y * 0.1f);
+                v4.z = v4.z + dt * (d4.z * 0.1f); v4.w = v4.w + dt * (d4.w * 0.1f);
+                zsts4(sv + i * FZ_PV + c0, v4);
+            }
+        }
+    };
+    {
+        const float4 none[FZ_R] = {};
+        frame_and_buoyancy(nullptr, true, none);
+    }
+    cluster_sync_all();          // every CTA of the cluster is past its loads before anybody stores into a neighbour
+
+    // gathers of back-traces that leave the stored rows: from the owner CTA's shared memory (its OWN rows are current)
+    auto far_u = [&](const int y, const int x) { const int rk = min(y / RB, NC - 1); return cluster_map(su_s, rk)[(y - (rk * RB - CH)) * FZ_PU + x]; };
+    auto far_v = [&](const int y, const int x) { const int rk = y / RB; return cluster_map(sv_s, rk)[(y - (rk * RB - CH)) * FZ_PV + x]; };
+    auto far_d = [&](const int y, const int x) { const int rk = y / RB; return cluster_map(sd_s, rk)[(y - (rk * RB - CH)) * FZ_PD + x]; };
+
+    for (int t = 0; t < a.nsteps; ++t) {
+        // ---- a4 diffusion of u, v, density: strip mapping, halo rows give the rows above / below the band          :158-160
+        {
+            float4 R[FZ_R];
+            float X = 0.f;
+            zdiffuse_strip<FZ_PU>(su, h + 1, w, a.c_uv, R, r0, c0, lane);
+            if (xu) X = zdiff_cell(su, FZ_PU, h + 1, w, 128, xe, a.c_uv);
+            cluster_sync_all();                       // everybody has read the old u (own rows and halo copies)
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r) cput4<FZ_PU>(fu, r0 + r, c0, R[r]);
+            if (xu) su[128 * FZ_PU + xe] = X;
+            zdiffuse_strip<FZ_PV>(sv, h, w + 1, a.c_uv, R, r0, c0, lane);
+            if (xv) X = zdiff_cell(sv, FZ_PV, h, w + 1, xr, 128, a.c_uv);
+            cluster_sync_all();
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r) cput4<FZ_PV>(fv, r0 + r, c0, R[r]);
+            if (xv) cput1<FZ_PV>(fv, xr, 128, X);
+            zdiffuse_strip<FZ_PD>(sd, h, w, a.c_d, R, r0, c0, lane);
+            cluster_sync_all();
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r) cput4<FZ_PD>(fd, r0 + r, c0, R[r]);
+            cluster_sync_all();                       // the new rows and halo rows are visible
+        }
+
+        // ---- a5 divergence into registers                                                                          :136
+        FzStrip ND = {};
+        {
+            float4 ua = zlds4(su + r0 * FZ_PU + c0);
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r) {
+                const int i = r0 + r;
+                const float4 ub = zlds4(su + (i + 1) * FZ_PU + c0);
+                const float4 va = zlds4(sv + i * FZ_PV + c0);
+                const float vr = sv[i * FZ_PV + c0 + 4];
+                float4 o;
+                o.x = ((ub.x - ua.x) + va.y) - va.x;
+                o.y = ((ub.y - ua.y) + va.z) - va.y;
+                o.z = ((ub.z - ua.z) + va.w) - va.z;
+                o.w = ((ub.w - ua.w) + vr) - va.w;
+                o = zdiv4(o, fzdiv);
+                packed_set_row(ND, r, make_float4(-o.x, -o.y, -o.z, -o.w));
+                ua = ub;
+            }
+        }
+
+        // ---- a6 K Jacobi sweeps: boundary rows first, posted to the neighbouring warps (shared memory) and CTAs (DSMEM),
+        //      cluster barrier arrive, interior rows, cluster barrier wait                                          :139-145
+        halo[0][0][warp][lane] = packed_row(P, 0);
+        halo[0][1][warp][lane] = packed_row(P, 7);
+        if (warp == 0 && xp_up) xp_up[0][1][lane] = packed_row(P, 0);
+        if (warp == NW - 1 && xp_dn) xp_dn[0][0][lane] = packed_row(P, 7);
+        cluster_sync_all();
+        {
+            FzStrip Q;
+            auto sweep = [&](const FzStrip& S, FzStrip& Dst, const int q) {
+                const float4 up = warp > 0 ? halo[q][1][warp - 1][lane] : (c > 0 ? xp[q][0][lane] : zero4);
+                const float4 dn = warp < NW - 1 ? halo[q][0][warp + 1][lane] : (!last_cta ? xp[q][1][lane] : zero4);
+                packed_pair<0, (FZ_PMASK & 1) != 0>(S, Dst, ND, up, dn, M);
+                packed_pair<3, (FZ_PMASK & 8) != 0>(S, Dst, ND, up, dn, M);
+                if (ringmask & 0x81u) {
+                    if (ringmask & 1u) packed_set_row(Dst, 0, zero4);
+                    if (ringmask & 0x80u) packed_set_row(Dst, 7, zero4);
+                }
+                const float4 n0 = packed_row(Dst, 0), n7 = packed_row(Dst, 7);
+                halo[q ^ 1][0][warp][lane] = n0;
+                halo[q ^ 1][1][warp][lane] = n7;
+                if (warp == 0 && xp_up) xp_up[q ^ 1][1][lane] = n0;
+                if (warp == NW - 1 && xp_dn) xp_dn[q ^ 1][0][lane] = n7;
+                cluster_arrive();
+                packed_pair<1, (FZ_PMASK & 2) != 0>(S, Dst, ND, up, dn, M);
+                packed_pair<2, (FZ_PMASK & 4) != 0>(S, Dst, ND, up, dn, M);
+                if (ringmask & 0x7eu) packed_zero_rows(Dst, ringmask & 0x7eu);
+                cluster_wait();
+            };
+            int s = 0;
+            for (; s + 1 < a.K; s += 2) {
+                sweep(P, Q, 0);
+                sweep(Q, P, 1);
+            }
+            if (s < a.K) {
+                sweep(P, Q, 0);
+                P = Q;
+            }
+        }
+
+        // ---- a7 gradient subtract on the owned rows, then the neighbours' halo rows of u and v                   :148-149
+        {
+            const int q = a.K & 1;
+            float4 pabove = warp > 0 ? halo[q][1][warp - 1][lane] : (c > 0 ? xp[q][0][lane] : zero4);
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r) {
+                const int i = r0 + r;
+                const float4 pc4 = packed_row(P, r);
+                const float pleft = __shfl_up_sync(0xffffffffu, pc4.w, 1);
+                float4 u4 = zlds4(su + i * FZ_PU + c0);
+                float4 v4 = zlds4(sv + i * FZ_PV + c0);
+                if (i >= 1) {
+                    u4.x = u4.x - dt * (pc4.x - pabove.x); u4.y = u4.y - dt * (pc4.y - pabove.y);
+                    u4.z = u4.z - dt * (pc4.z - pabove.z); u4.w = u4.w - dt * (pc4.w - pabove.w);
+                }
+                if (c0 >= 1) v4.x = v4.x - dt * (pc4.x - pleft);
+                v4.y = v4.y - dt * (pc4.y - pc4.x); v4.z = v4.z - dt * (pc4.z - pc4.y); v4.w = v4.w - dt * (pc4.w - pc4.z);
+                cput4<FZ_PU>(fu, i, c0, u4);
+                cput4<FZ_PV>(fv, i, c0, v4);
+                pabove = pc4;
+            }
+        }
+        cluster_sync_all();
+
+        float4 mrow[FZ_R] = {};
+        // ---- a10/a11 advection (cyclic mapping): u by (u, v); v by (u', v); density by (u', v'), decay              :166-171
+        {
+            float2 R[FZ_R][2];
+            float X = 0.f;
+            const float ulo = (float)slo, uhi = (float)shi_u, chi = (float)shi_c;
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r)
+#pragma unroll
+                for (int kp = 0; kp < 2; ++kp)
+                    R[r][kp] = cadvect_pair<FZ_PU, false, NC>(su, h + 1, w, su, sv, r0 + r, lane + 64 * kp, dt, 1.0f, ulo, uhi, far_u);
+            if (xu) X = zadvect_cell<FZ_PU>(su, h + 1, w, su, sv, h, w, 128, xe, dt);       // row 128 back-traces to itself (zero velocity there)
+            cluster_sync_all();                       // every gather of the cluster (near and far) is done
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r)
+#pragma unroll
+                for (int kp = 0; kp < 2; ++kp) {
+                    const int i = r0 + r, j = lane + 64 * kp;
+                    cput1<FZ_PU>(fu, i, j, R[r][kp].x);
+                    cput1<FZ_PU>(fu, i, j + 32, R[r][kp].y);
+                }
+            if (xu) su[128 * FZ_PU + xe] = X;
+            cluster_sync_all();
+
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r)
+#pragma unroll
+                for (int kp = 0; kp < 2; ++kp)
+                    R[r][kp] = cadvect_pair<FZ_PV, false, NC>(sv, h, w + 1, su, sv, r0 + r, lane + 64 * kp, dt, 1.0f, ulo, chi, far_v);
+            // the staggered column 128 of v: both interpolated velocities are zero there (navier_stokes.py:97-109), so the cell
+            // back-traces to itself and only touches its own row
+            if (xv) X = zadvect_cell<FZ_PV>(sv, h, w + 1, su, sv, h, w, xr, 128, dt);
+            cluster_sync_all();
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r)
+#pragma unroll
+                for (int kp = 0; kp < 2; ++kp) {
+                    const int i = r0 + r, j = lane + 64 * kp;
+                    cput1<FZ_PV>(fv, i, j, R[r][kp].x);
+                    cput1<FZ_PV>(fv, i, j + 32, R[r][kp].y);
+                }
+            if (xv) cput1<FZ_PV>(fv, xr, 128, X);
+            cluster_sync_all();
+
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r)
+#pragma unroll
+                for (int kp = 0; kp < 2; ++kp)
+                    R[r][kp] = cadvect_pair<FZ_PD, true, NC>(sd, h, w, su, sv, r0 + r, lane + 64 * kp, dt, a.decay, ulo, chi, far_d);
+            cluster_sync_all();
+            if (a.frames && a.fmul) {
+#pragma unroll
+                for (int r = 0; r < FZ_R; ++r) mrow[r] = __ldg(reinterpret_cast<const float4*>(a.fmul + (size_t)(r0 + r) * pc + c0));
+            }
+#pragma unroll
+            for (int r = 0; r < FZ_R; ++r)
+#pragma unroll
+                for (int kp = 0; kp < 2; ++kp) {
+                    const int i = r0 + r, j = lane + 64 * kp;
+                    cput1<FZ_PD>(fd, i, j, R[r][kp].x);
+                    cput1<FZ_PD>(fd, i, j + 32, R[r][kp].y);
+                }
+            cluster_sync_all();
+        }
+
+        // ---- a11 returned copy of this step + buoyancy of the next
+        float* frame = a.frames ? a.frames + b * a.frame_batch_stride + (size_t)t * a.frame_step_stride : nullptr;
+        frame_and_buoyancy(frame, t + 1 < a.nsteps, mrow);
+        __syncthreads();
+    }
+
+    // ---- write back the owned rows: pressure from registers, u, v, density from shared memory ------------------------------
+#pragma unroll
+    for (int r = 0; r < FZ_R; ++r) *reinterpret_cast<float4*>(gP + (size_t)(r0 + r) * pc + c0) = packed_row(P, r);
+    {
+        const int first = c * RB;
+        for (int k = tid; k < (fu.last - first + 1) * (pu / 4); k += NT) {
+            const int i = first + k / (pu / 4), g = k % (pu / 4);
+            *reinterpret_cast<float4*>(gU + (size_t)i * pu + 4 * g) = zlds4(su + i * FZ_PU + 4 * g);
+        }
+        for (int k = tid; k < RB * (pv / 4); k += NT) {
+            const int i = first + k / (pv / 4), g = k % (pv / 4);
+            *reinterpret_cast<float4*>(gV + (size_t)i * pv + 4 * g) = zlds4(sv + i * FZ_PV + 4 * g);
+        }
+        for (int k = tid; k < RB * (pc / 4); k += NT) {
+            const int i = first + k / (pc / 4), g = k % (pc / 4);
+            *reinterpret_cast<float4*>(gD + (size_t)i * pc + 4 * g) = zlds4(sd + i * FZ_PD + 4 * g);
+        }
+    }
+    cluster_sync_all();          // no CTA leaves (and frees its shared memory) while a neighbour may still read or write it
+}
+
 // does the current device give one CTA the 226.5 KB the fused kernel needs (B200: 227 KB)?
 static bool device_has_room()
 {
@@ -683,6 +1162,48 @@ int fused_plan(int nsims, int nsteps, int piece_len, int32_t* items, int capacit
     return SMK_OK;
 }
 
+// CTAs per simulation for a call of `batch` full-size (128 x 128) simulations: 0 = one CTA per simulation (k_step_fused), 2 or 4 =
+// k_step_cluster.  A cluster pays when the simulations would leave most SMs idle: up to 33 simulations fit four CTAs each (the
+// hardware co-schedules 33 clusters of 4 on the 148 SMs of a B200), up to 74 two each.  SMK_FUSED_CLUSTER = 0 / 2 / 4 forces.
+static int pick_cluster(const int batch)
+{
+    int nsm = 0, dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) return 0;
+    const int forced = env().fused_cluster;
+    if (forced != SMK_ENV_UNSET) return (forced == 2 || forced == 4) ? forced : 0;
+    if (batch * 4 <= (nsm / 4 - 4) * 4) return 4;         // 148 SMs: 33 clusters of four
+    if (batch * 2 <= nsm) return 2;
+    return 0;
+}
+
+template <int NC>
+static int launch_cluster_nc(const int batch, const FusedArgs& a, cudaStream_t s)
+{
+    typedef ClusterCfg<NC> C;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 63;
+    if (!attr_set[dev] || dev == 63) {
+        const cudaError_t e = cudaFuncSetAttribute(k_step_cluster<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return fail((int)e, "k_step_cluster: cannot opt in to %zu B of shared memory: %s", (size_t)C::SMEM, cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)batch * NC); cfg.blockDim = dim3(C::NT); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = s;
+    cudaLaunchAttribute attr = {};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = NC; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    ProfScope prof_(SMK_PH_STEP_FUSED, s);
+    (void)cudaLaunchKernelEx(&cfg, k_step_cluster<NC>, a);
+    return check_launch("k_step_cluster");
+}
+
+static int launch_cluster(const int nc, const int batch, const FusedArgs& a, cudaStream_t s)
+{
+    return nc == 4 ? launch_cluster_nc<4>(batch, a, s) : launch_cluster_nc<2>(batch, a, s);
+}
+
 int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float* p, int nsteps, float* frames,
                        int64_t frame_step_stride, int64_t frame_batch_stride, const float* fmul,
                        float dt, float c_uv, float c_d, float decay, int K, float* scratch, cudaStream_t s)
@@ -707,6 +1228,10 @@ int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float*
     a.frame_step_stride = frame_step_stride; a.frame_batch_stride = frame_batch_stride;
     a.dt = dt; a.c_uv = c_uv; a.c_d = c_d; a.decay = decay; a.K = K; a.nsteps = nsteps;
     a.items = nullptr; a.progress = nullptr; a.ticket = nullptr; a.spin_budget = 1u << 25;
+    if (full) {
+        const int nc = pick_cluster(g->batch);
+        if (nc) return launch_cluster(nc, g->batch, a, s);
+    }
     int ctas = g->batch;
     const int seg_len = pick_seg_len(g, nsteps, scratch, s);
     if (seg_len > 0) {

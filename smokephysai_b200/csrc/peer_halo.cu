@@ -76,8 +76,15 @@ k_halo_xfer(const HxArgs a)
     const HxCopy c = a.c[blockIdx.y];
     const float4* __restrict__ src = c.src + (c.parity_on_dst ? 0 : poff);
     float4* __restrict__ dst = c.dst + (c.parity_on_dst ? poff : 0);
-    for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < c.n4; k += (long long)gridDim.x * 256)
-        dst[k] = PUSH ? src[k] : __ldcg(src + k);          // the mailbox is written by another GPU: never through this SM's L1
+    // four independent 16-byte loads in flight per thread (a copy is ~50 k of them at eight slabs of 8192 columns: latency, not
+    // bandwidth, is what a short copy pays).  The mailbox is written by another GPU: it is never read through this SM's L1.
+    const long long stride = (long long)gridDim.x * 256;
+    long long k = (long long)blockIdx.x * 256 + threadIdx.x;
+    for (; k + 3 * stride < c.n4; k += 4 * stride) {
+        const float4 v0 = __ldcg(src + k), v1 = __ldcg(src + k + stride), v2 = __ldcg(src + k + 2 * stride), v3 = __ldcg(src + k + 3 * stride);
+        dst[k] = v0; dst[k + stride] = v1; dst[k + 2 * stride] = v2; dst[k + 3 * stride] = v3;
+    }
+    for (; k < c.n4; k += stride) dst[k] = __ldcg(src + k);
     // last CTA out: publish (push) / count the exchange (unpack)
     if (PUSH) __threadfence_system();
     __syncthreads();
@@ -140,8 +147,8 @@ static int peer_xfer(const smk_peer_comm_t* c, float* const* base, bool push, cu
     if (a.n == 0) return SMK_OK;                             // no neighbour at all (world of one)
     long long most = 0;
     for (int k = 0; k < a.n; ++k) most = most > a.c[k].n4 ? most : a.c[k].n4;
-    int per = (int)((most + 256 * 8 - 1) / (256 * 8));       // eight 16-byte elements per thread
-    per = per < 1 ? 1 : (per > 16 ? 16 : per);               // at most 8 x 16 = 128 CTAs: one wave, all co-resident
+    int per = (int)((most + 256 * 4 - 1) / (256 * 4));       // four 16-byte elements per thread
+    per = per < 1 ? 1 : (per > 32 ? 32 : per);               // at most 8 x 32 = 256 CTAs of 256 threads: all co-resident (2 per SM)
     ProfScope prof_(SMK_PH_HALO, s);
     if (push) launch_chain(k_halo_xfer<true>, dim3(per, a.n), dim3(256), 0, s, a);
     else      launch_chain(k_halo_xfer<false>, dim3(per, a.n), dim3(256), 0, s, a);
@@ -169,18 +176,26 @@ using namespace smk;
 
 // The tail of a step on a (slab) grid whose live u, v, density are the outputs of forces + diffusion and whose live p holds the
 // K sweeps: gradient subtract (navier_stokes.py:148-149), sequential advection of u, v, density (:166-168), decay (:171).
-// The live copies flip (u, v, density end up in the other copy).  On big fields the gradient subtract runs inside the u and v
-// advections (k_advect_tiled<.., 1 / 2>, stencil.cu); else k_project runs on its own first.
+// The live copies of u and density flip; so does v's, except on big fields, where the gradient subtract runs inside the u
+// advection (k_advect_tiled<.., 1>, stencil.cu), the projected v passes through the spare copy and the live v ends where it was.
 static int project_advect(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
                           const smk_slab_check_t* chk_u, const smk_slab_check_t* chk_v, const smk_slab_check_t* chk_d, cudaStream_t s)
 {
     const int cu = st->cur_u, cv = st->cur_v, cd = st->cur_d;
     float *u1 = st->u[cu], *u0 = st->u[cu ^ 1], *v1 = st->v[cv], *v0 = st->v[cv ^ 1], *d1 = st->d[cd], *d0 = st->d[cd ^ 1];
     const float* pl = st->p[st->cur_p];
-    const bool fuse = advect_can_fuse_project(g);
-    if (!fuse) SMK_TRY_(launch_project(g, pl, u1, v1, prm->dt, s));
-    SMK_TRY_(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, 0, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, chk_u, s, fuse ? 1 : 0, pl));
-    SMK_TRY_(launch_advect(g, v1, v0, g->h, g->w + 1, g->pitch_v, 0, u0, v1, prm->dt, 1.0f, nullptr, 0, nullptr, chk_v, s, fuse ? 2 : 0, pl));
+    if (advect_can_fuse_project(g)) {
+        // u advection with the gradient subtract inside; it leaves the projected v in the spare copy v0, so the v advection runs
+        // v0 -> v1 and the live v stays in the copy it was in
+        SMK_TRY_(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, 0, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, chk_u, s, 1, pl, v0));
+        SMK_TRY_(launch_advect(g, v0, v1, g->h, g->w + 1, g->pitch_v, 0, u0, v0, prm->dt, 1.0f, nullptr, 0, nullptr, chk_v, s));
+        SMK_TRY_(launch_advect(g, d1, d0, g->h, g->w, g->pitch_c, 0, u0, v1, prm->dt, prm->decay, nullptr, 0, nullptr, chk_d, s));
+        st->cur_u = cu ^ 1; st->cur_d = cd ^ 1;
+        return SMK_OK;
+    }
+    SMK_TRY_(launch_project(g, pl, u1, v1, prm->dt, s));
+    SMK_TRY_(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, 0, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, chk_u, s));
+    SMK_TRY_(launch_advect(g, v1, v0, g->h, g->w + 1, g->pitch_v, 0, u0, v1, prm->dt, 1.0f, nullptr, 0, nullptr, chk_v, s));
     SMK_TRY_(launch_advect(g, d1, d0, g->h, g->w, g->pitch_c, 0, u0, v0, prm->dt, prm->decay, nullptr, 0, nullptr, chk_d, s));
     st->cur_u = cu ^ 1; st->cur_v = cv ^ 1; st->cur_d = cd ^ 1;
     return SMK_OK;

@@ -381,7 +381,8 @@ struct AdvectArgs {
     unsigned ngroups; unsigned long long magic;          // row = (idx * magic) >> 40 == idx / ngroups (+ fix-up)
     int row0, gh;                                        // slab: global row of local row 0, global cell rows
     int need_lo, need_hi, valid_lo, valid_hi; int* overflow;
-    const float* P; int pc; long long sc_;               // k_advect_tiled<.., PROJ>: pressure for the fused gradient subtract
+    const float* P; int pc; long long sc_;               // k_advect_tiled<.., 1>: pressure for the fused gradient subtract,
+    float* Vout;                                         // and where the projected v goes (a different array than V)
 };
 
 template <bool SLAB>
@@ -510,21 +511,22 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_sr
 __device__ __forceinline__ float2 neg2(const float2 a) { return make_float2(-a.x, -a.y); }
 
 // One value of the advected field straight from global memory (the rare back-trace that leaves the staged window), with the
-// gradient subtract applied on the fly when the kernel fuses it (PROJ 1: the field is u, 2: the field is v).
+// gradient subtract applied on the fly when the kernel fuses it (PROJ 1: the field is u).
 template <int PROJ>
 __device__ __forceinline__ float advect_global(const AdvectArgs& a, const float* F, const float* P, const int y, const int x)
 {
     float f = __ldg(F + ((unsigned)y * a.pitch + x));
     if (PROJ == 1 && y >= 1 && y <= a.h - 1 && x < a.w) f = f - a.dt * (__ldg(P + ((unsigned)y * a.pc + x)) - __ldg(P + ((unsigned)(y - 1) * a.pc + x)));
-    if (PROJ == 2 && x >= 1 && x <= a.w - 1 && y < a.h) f = f - a.dt * (__ldg(P + ((unsigned)y * a.pc + x)) - __ldg(P + ((unsigned)y * a.pc + x - 1)));
     return f;
 }
 
-// PROJ: 0 plain advection; 1 / 2: k_project fused in -- the staged u (1: the field window and the u tile) and v (1 and 2: the
-// v tile; 2: the field window) are the UNPROJECTED arrays and get u -= dt (p[i][j] - p[i-1][j]), v -= dt (p[i][j] - p[i][j-1])
-// in shared memory, from a pressure window staged next to them, before the advection reads them.  Same two rounded operations
-// per cell as k_project, so the result is bit-identical to project-then-advect; the projected u is never written to memory
-// (only the u advection reads it) and the projected v is recomputed by the v advection (PROJ 2) instead of being written.
+// PROJ: 0 plain advection; 1: k_project fused into the u advection -- the staged u (the field window, which is also where an
+// interior tile takes its u samples from) and the v tile are the UNPROJECTED arrays and get u -= dt (p[i][j] - p[i-1][j]),
+// v -= dt (p[i][j] - p[i][j-1]) in shared memory, from a pressure window staged next to them, before the advection reads them.
+// Same two rounded operations per cell as k_project, so the result is bit-identical to project-then-advect.  The projected u is
+// never written to memory (only this kernel reads it); the projected v tile is written to a.Vout, a DIFFERENT array than the
+// one being read (other CTAs still stage unprojected rows of V), which the v and density advections then use.  A first version
+// that let the v advection re-project v from p instead (no Vout) was slower: 274 against 177 us per launch at 8192^2.
 template <bool SLAB, bool INTERIOR, int PROJ>
 __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, float (*sP)[AT_PP], const float* F, const float* U, const float* V,
                                             const float* P, float* O, const size_t b, const int i0, const int j0)
@@ -546,8 +548,9 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
         }
     }
     const int urows = a.h + 1;
+    // (an interior tile of the fused u advection reads its u samples from the projected field window instead: same array)
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
+    for (int rr = 0; rr < ((PROJ == 1 && INTERIOR) ? 0 : 2); ++rr) {
         const int r = wp + 8 * rr, y = i0 + r;
         if (INTERIOR || y < urows) {
             const float* src = U + ((unsigned)y * a.pu + j0);
@@ -578,31 +581,59 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (PROJ) {
+    if (PROJ && INTERIOR) {
+        // every staged cell is one k_project updates: four cells per LDS.128 / STS.128, no predicate
+        const float dt = a.dt;
+        for (int k = tid; k < AT_FR * (AT_FP / 4); k += 256) {                       // field window, 24 rows x 34 groups
+            const int r = k / (AT_FP / 4), c = (k - r * (AT_FP / 4)) * 4;
+            float4 f = *reinterpret_cast<const float4*>(&T.sF[r][c]);
+            const float4 pc = *reinterpret_cast<const float4*>(&sP[r + 1][c + 4]);
+            const float4 pa = *reinterpret_cast<const float4*>(&sP[r][c + 4]);
+            f.x = f.x - dt * (pc.x - pa.x); f.y = f.y - dt * (pc.y - pa.y);
+            f.z = f.z - dt * (pc.z - pa.z); f.w = f.w - dt * (pc.w - pa.w);
+            *reinterpret_cast<float4*>(&T.sF[r][c]) = f;
+        }
+        for (int k = tid; k < (AT_R + 1) * (AT_C / 4); k += 256) {                   // v tile, 17 rows x 32 groups
+            const int r = k / (AT_C / 4), c = (k - r * (AT_C / 4)) * 4;
+            float4 f = *reinterpret_cast<const float4*>(&T.sV[r][c]);
+            const float4 pc = *reinterpret_cast<const float4*>(&sP[r + 5][c + 8]);
+            const float pl = sP[r + 5][c + 7];
+            f.x = f.x - dt * (pc.x - pl); f.y = f.y - dt * (pc.y - pc.x);
+            f.z = f.z - dt * (pc.z - pc.y); f.w = f.w - dt * (pc.w - pc.z);
+            *reinterpret_cast<float4*>(&T.sV[r][c]) = f;
+            if (r < AT_R) *reinterpret_cast<float4*>(a.Vout + b * a.sv_ + ((unsigned)(i0 + r) * a.pv + j0 + c)) = f;      // the tile's own 16 rows
+        }
+        __syncthreads();
+    } else if (PROJ) {
         const float dt = a.dt;
         // field window: row r <-> y = i0 - 4 + r <-> sP row r + 1; column c <-> x = j0 - 4 + c <-> sP column c + 4
         for (int k = tid; k < AT_FR * AT_FP; k += 256) {
             const int r = k / AT_FP, c = k - r * AT_FP, y = i0 - AT_HB + r, x = j0 - AT_HB + c;
-            if (PROJ == 1) {
-                if (INTERIOR || (y >= 1 && y <= a.h - 1 && x >= 0 && x < w))
-                    T.sF[r][c] = T.sF[r][c] - dt * (sP[r + 1][c + 4] - sP[r][c + 4]);
-            } else {
-                if (INTERIOR || (y >= 0 && y < a.h && x >= 1 && x <= w - 1))
-                    T.sF[r][c] = T.sF[r][c] - dt * (sP[r + 1][c + 4] - sP[r + 1][c + 3]);
-            }
+            if (y >= 1 && y <= a.h - 1 && x >= 0 && x < w)
+                T.sF[r][c] = T.sF[r][c] - dt * (sP[r + 1][c + 4] - sP[r][c + 4]);
         }
-        if (PROJ == 1)                                   // u tile: row r <-> y = i0 + r <-> sP row r + 5; column c <-> x = j0 + c <-> sP column c + 8
-            for (int k = tid; k < AT_R * (AT_C + 1); k += 256) {
-                const int r = k / (AT_C + 1), c = k - r * (AT_C + 1), y = i0 + r, x = j0 + c;
-                if (INTERIOR || (y >= 1 && y <= a.h - 1 && x < w))
-                    T.sU[r][c] = T.sU[r][c] - dt * (sP[r + 5][c + 8] - sP[r + 4][c + 8]);
-            }
+        // u tile: row r <-> y = i0 + r <-> sP row r + 5; column c <-> x = j0 + c <-> sP column c + 8
+        for (int k = tid; k < AT_R * (AT_C + 1); k += 256) {
+            const int r = k / (AT_C + 1), c = k - r * (AT_C + 1), y = i0 + r, x = j0 + c;
+            if (y >= 1 && y <= a.h - 1 && x < w)
+                T.sU[r][c] = T.sU[r][c] - dt * (sP[r + 5][c + 8] - sP[r + 4][c + 8]);
+        }
         for (int k = tid; k < (AT_R + 1) * AT_C; k += 256) {     // v tile
             const int r = k / AT_C, c = k - r * AT_C, y = i0 + r, x = j0 + c;
-            if (INTERIOR || (y < a.h && x >= 1 && x <= w - 1))
+            if (y < a.h && x >= 1 && x <= w - 1)
                 T.sV[r][c] = T.sV[r][c] - dt * (sP[r + 5][c + 8] - sP[r + 5][c + 7]);
         }
         __syncthreads();
+        // the projected v of the tile's own rows (every staged 16-byte chunk: cells, column w, padding) goes to Vout ...
+        float* vout = a.Vout + b * a.sv_;
+        for (int k = tid; k < AT_R * (AT_C / 4); k += 256) {
+            const int r = k / (AT_C / 4), c = (k - r * (AT_C / 4)) * 4, y = i0 + r, x = j0 + c;
+            if (y < a.h && x < a.pv) *reinterpret_cast<float4*>(vout + ((unsigned)y * a.pv + x)) = *reinterpret_cast<const float4*>(&T.sV[r][c]);
+        }
+        // ... and where w is a multiple of the tile width, column w of v (which k_project leaves alone) and its padding lie
+        // beyond the last tile column of u: the tiles of that column copy them
+        if (j0 + AT_C == w && tid < AT_R && i0 + tid < a.h)
+            *reinterpret_cast<float4*>(vout + ((unsigned)(i0 + tid) * a.pv + w)) = __ldg(reinterpret_cast<const float4*>(V + ((unsigned)(i0 + tid) * a.pv + w)));
     }
 
     // slab: h is the GLOBAL cell-row count and gi the global row of this thread's cells; memory stays local
@@ -622,6 +653,7 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
         const bool urow_ok = INTERIOR || gi <= h - 1;                              // u_i is 0 on u's last row     :97-102
         const bool vrow_ok = INTERIOR || (gi <= h - 2 && (!SLAB || i + 1 < a.h));  // v_i is 0 on the last cell row :104-109
         float val[4];
+        const float* urow = (PROJ == 1 && INTERIOR) ? &T.sF[ri + AT_HB][AT_HB] : &T.sU[ri][0];
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {
             const int c = lane + 64 * kp, c1 = c + 32;                 // tile columns of the pair
@@ -629,8 +661,8 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
             // a9: u_i = 0.5*U[i][j] + 0.5*U[i][j+1] for j <= w-2;  v_i = 0.5*V[i][j] + 0.5*V[i+1][j] for j <= w-1; else 0
             const bool cu0 = urow_ok && (INTERIOR || j <= w - 2), cu1 = urow_ok && (INTERIOR || j1 <= w - 2);
             const bool cv0 = vrow_ok && (INTERIOR || j <= w - 1), cv1 = vrow_ok && (INTERIOR || j1 <= w - 1);
-            const float2 ua = make_float2(cu0 ? T.sU[ri][c] : 0.f, cu1 ? T.sU[ri][c1] : 0.f);
-            const float2 ub = make_float2(cu0 ? T.sU[ri][c + 1] : 0.f, cu1 ? T.sU[ri][c1 + 1] : 0.f);
+            const float2 ua = make_float2(cu0 ? urow[c] : 0.f, cu1 ? urow[c1] : 0.f);
+            const float2 ub = make_float2(cu0 ? urow[c + 1] : 0.f, cu1 ? urow[c1 + 1] : 0.f);
             const float2 va = make_float2(cv0 ? T.sV[ri][c] : 0.f, cv1 ? T.sV[ri][c1] : 0.f);
             const float2 vb = make_float2(cv0 ? T.sV[ri + 1][c] : 0.f, cv1 ? T.sV[ri + 1][c1] : 0.f);
             const float2 hua = __fmul2_rn(half2, ua), hub = __fmul2_rn(half2, ub);
@@ -799,9 +831,9 @@ k_advect_tiled(const AdvectArgs a)
     else          advect_tile<SLAB, false, PROJ>(a, T, sP, F, U, V, P, O, b, i0, j0);
 }
 
-// proj / p: 0 / NULL for the plain advection; 1 (the field is u) or 2 (the field is v) fuses the gradient subtract of the pressure p
-// into the tiled kernel (u, v and the field are then the UNPROJECTED arrays).  advect_can_fuse_project() tells whether the launch
-// would take the tiled kernel; callers that get `false` run k_project first and pass proj = 0.
+// proj / p / vout: 0 / NULL / NULL for the plain advection; 1 fuses the gradient subtract of the pressure p into the tiled u
+// advection (field == u and v are then the UNPROJECTED arrays; the projected v is written to vout, a different array).
+// advect_can_fuse_project() tells whether the launch would take the tiled kernel; callers that get `false` run k_project first.
 bool advect_can_fuse_project(const smk_grid_t* g)
 {
     if (env().project_fused == 0) return false;
@@ -813,7 +845,7 @@ bool advect_can_fuse_project(const smk_grid_t* g)
 
 int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows, int cols, int pitch, int64_t stride,
                   const float* u, const float* v, float dt, float scale, float* frame, int64_t frame_stride,
-                  const float* fmul, const smk_slab_check_t* chk, cudaStream_t s, int proj, const float* p)
+                  const float* fmul, const smk_slab_check_t* chk, cudaStream_t s, int proj, const float* p, float* vout)
 {
     if ((int64_t)rows * pitch >= (1ll << 31)) return fail(SMK_EUNSUPPORTED, "smk_advect: field of %d x %d exceeds 2^31 elements", rows, pitch);
     AdvectArgs a;
@@ -827,16 +859,17 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
     a.row0 = g->row0; a.gh = g->gh;
     a.need_lo = chk ? chk->need_lo : 0; a.need_hi = chk ? chk->need_hi : 0;
     a.valid_lo = chk ? chk->valid_lo : 0; a.valid_hi = chk ? chk->valid_hi : 0; a.overflow = chk ? chk->overflow_flag : nullptr;
-    a.P = p; a.pc = g->pitch_c; a.sc_ = g->stride_c;
+    a.P = p; a.pc = g->pitch_c; a.sc_ = g->stride_c; a.Vout = vout;
     const unsigned long long nthreads = (unsigned long long)rows * a.ngroups;
     dim3 grid((unsigned)((nthreads + 255) / 256), g->batch);
     if (proj) {
-        if (!p || (proj != 1 && proj != 2) || !advect_can_fuse_project(g)) return fail(SMK_EINVAL, "launch_advect: fused gradient subtract needs p and the tiled kernel");
-        ProfScope prof_(proj == 1 ? SMK_PH_PROJECT_ADVECT_U : SMK_PH_ADVECT_V, s);
+        if (!p || !vout || vout == v || proj != 1 || rows != g->h + 1 || !advect_can_fuse_project(g))
+            return fail(SMK_EINVAL, "launch_advect: the fused gradient subtract is for the u advection on the tiled kernel, and needs p and a separate array for the projected v");
+        ProfScope prof_(SMK_PH_PROJECT_ADVECT_U, s);
         dim3 tgrid((unsigned)((pitch + AT_C - 1) / AT_C), (unsigned)((rows + AT_R - 1) / AT_R), g->batch);
         const bool slab_ = g->gh != 0 && (g->gh != g->h || g->row0 != 0);
-        if (proj == 1) { if (slab_) launch_chain(k_advect_tiled<true, 1>, tgrid, dim3(256), 0, s, a); else launch_chain(k_advect_tiled<false, 1>, tgrid, dim3(256), 0, s, a); }
-        else           { if (slab_) launch_chain(k_advect_tiled<true, 2>, tgrid, dim3(256), 0, s, a); else launch_chain(k_advect_tiled<false, 2>, tgrid, dim3(256), 0, s, a); }
+        if (slab_) launch_chain(k_advect_tiled<true, 1>, tgrid, dim3(256), 0, s, a);
+        else       launch_chain(k_advect_tiled<false, 1>, tgrid, dim3(256), 0, s, a);
         return check_launch("k_advect_tiled (fused gradient subtract)");
     }
     ProfScope prof_(rows == g->h + 1 ? SMK_PH_ADVECT_U : (cols == g->w + 1 ? SMK_PH_ADVECT_V : SMK_PH_ADVECT_D), s);

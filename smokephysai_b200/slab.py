@@ -224,6 +224,30 @@ class NcclExchanger:
 FIELD_ORDER = ("u", "v", "d", "p")          # smk_peer_comm_t field order
 
 
+def peer_links(geom, pitch):
+    """Pure host arithmetic of the peer exchange: {side: {field: (send_off, send_count, recv_off, recv_count)}} in fp32
+    elements relative to the base of each field, side 0 = upper neighbour (rank - 1), 1 = lower (rank + 1); pitch maps the
+    field names u / v / d / p to their row pitch.  What one rank sends on a side is what its neighbour receives on the
+    opposite side (tests/test_slab_host.py drives a numpy mailbox with these numbers against the plain halo copy)."""
+    out = {}
+    for side, peer in ((0, geom.rank - 1), (1, geom.rank + 1)):
+        if not (0 <= peer < geom.world):
+            continue
+        link = {}
+        for name in FIELD_ORDER:
+            sends, recvs = geom.blocks("u" if name == "u" else "c")
+            so = sc = ro = rc = 0
+            for p_, a, n in sends:
+                if p_ == peer:
+                    so, sc = a * pitch[name], n * pitch[name]
+            for p_, a, n in recvs:
+                if p_ == peer:
+                    ro, rc = a * pitch[name], n * pitch[name]
+            link[name] = (so, sc, ro, rc)
+        out[side] = link
+    return out
+
+
 class PeerExchanger:
     """Halo exchange by direct peer stores over NVLink (include/smoke_b200.h: smk_peer_*, csrc/peer_halo.cu).
 
@@ -314,15 +338,9 @@ class PeerExchanger:
             link.remote_flag = self._counter(bases[peer], 1 - side)
             link.local_mailbox = self._region(mine, side)
             link.local_flag = self._counter(mine, side)
+            numbers = peer_links(g, self.pitch)[side]
             for f, name in enumerate(FIELD_ORDER):
-                sends, recvs = g.blocks("u" if name == "u" else "c")
-                pitch = self.pitch[name]
-                for p_, a, n in sends:
-                    if p_ == peer:
-                        link.send_off[f], link.send_count[f] = a * pitch, n * pitch
-                for p_, a, n in recvs:
-                    if p_ == peer:
-                        link.recv_off[f], link.recv_count[f] = a * pitch, n * pitch
+                link.send_off[f], link.send_count[f], link.recv_off[f], link.recv_count[f] = numbers[name]
         self.comm = comm
 
     def _bases(self, named):

@@ -257,3 +257,38 @@ def test_fused_time_sliced_hand_over_with_a_co_resident_kernel():
     assert_same(out["2"][0], out["0"][0], "frames, sliced under contention vs classic")
     for k in FIELDS:
         assert_same(out["2"][1][k], out["0"][1][k], k + ", sliced under contention vs classic")
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("nc", [2, 4])
+@pytest.mark.parametrize("B,n,K,vel", [(1, 3, 20, 40.0), (3, 4, 7, 900.0), (5, 2, 40, 150.0)])
+def test_cluster_kernel_equals_oracle_and_one_cta_kernel(nc, B, n, K, vel):
+    """k_step_cluster: one 128 x 128 simulation on a cluster of 2 or 4 CTAs (rows split over the CTAs, halo rows and the Jacobi
+    boundary rows through distributed shared memory).  Frames and fields must equal the one-CTA-per-simulation kernel and the
+    oracle bit for bit; vel = 900 with dt = 0.02 back-traces up to 9 cells, past the two halo rows a CTA keeps, so those
+    gathers read the owner CTA's shared memory; K = 7 ends on the odd-sweep tail."""
+    h = w = 128
+    states = [random_state(h, w, 700 + 10 * nc + b, vel=vel) for b in range(B)]
+    out = {}
+    for mode in ("0", str(nc)):
+        with smk_env(SMK_FUSED_CLUSTER=mode, SMK_FUSED_SLICE=0):
+            ns = make(h, w, 0.02, 0.004, K, batch=B, step_kernel="fused")
+            for k in FIELDS:
+                setattr(ns, k, T(np.stack([st[k] for st in states])) if B > 1 else T(states[0][k]))
+            fmul = torch.linspace(0.0, 0.05, h * ns._layout.pitch_c, device="cuda").view(h, ns._layout.pitch_c)
+            n0 = _lib.launch_count()
+            frames = ns.run_steps(n, fmul=fmul)
+            assert _lib.launch_count() - n0 == 1
+            torch.cuda.synchronize()
+            out[mode] = (N(frames), {k: N(getattr(ns, k)) for k in FIELDS})
+    assert_same(out[str(nc)][0], out["0"][0], "frames, cluster of %d vs one CTA" % nc)
+    for k in FIELDS:
+        assert_same(out[str(nc)][1][k], out["0"][1][k], k + ", cluster of %d vs one CTA" % nc)
+    ref = oracle.OracleSolver((h, w), 0.02, 0.004, K)
+    for k in FIELDS:
+        setattr(ref, k, states[B - 1][k].copy())
+    for _ in range(n):
+        ref.step()
+    for k in FIELDS:
+        got = out[str(nc)][1][k]
+        assert_same(got[B - 1] if B > 1 else got, getattr(ref, k), k + " vs oracle")

@@ -158,3 +158,40 @@ def test_world2_gloo_slabs_match_undecomposed_oracle(tmp_path):
     for k in ("u", "v", "p", "d"):
         got = np.concatenate([p[k] for p in parts], axis=0)
         assert np.array_equal(got, want[k]), k
+
+
+@pytest.mark.parametrize("H,W,world,halo", [(64, 40, 2, 6), (100, 33, 3, 9), (256, 130, 4, 14), (1024, 20, 8, 24)])
+def test_peer_mailbox_arithmetic_equals_the_plain_halo_copy(H, W, world, halo):
+    """The offsets / counts PeerExchanger hands to smk_peer_push / smk_peer_unpack (slab.peer_links), driven through a numpy
+    model of the mailboxes (two parity slots per neighbour, four field regions per slot, a rank writes into the region its
+    neighbour reserves for the OPPOSITE side), must move exactly the rows local_exchange moves -- u's extra staggered row and
+    v's wider pitch included -- over several exchanges so that both parity slots are reused."""
+    from smokephysai_b200.navier_stokes import FieldLayout
+    from smokephysai_b200.slab import FIELD_ORDER, peer_links
+    geoms = [SlabGeometry(H, W, world, r, halo) for r in range(world)]
+    lay = [FieldLayout(g.hl, W) for g in geoms]
+    pitch = {"u": lay[0].pitch_u, "v": lay[0].pitch_v, "d": lay[0].pitch_c, "p": lay[0].pitch_c}
+    field_stride = (halo + 1) * max(pitch.values())
+    links = [peer_links(g, pitch) for g in geoms]
+    rng = np.random.default_rng(world)
+    rows = lambda g, n: g.hl + (1 if n == "u" else 0)
+    mail = [np.full((2, 2, 4, field_stride), np.nan, np.float32) for _ in range(world)]       # [side][slot][field][elements]
+    for seq in range(5):
+        flat = [{n: rng.standard_normal(rows(g, n) * pitch[n]).astype(np.float32) for n in FIELD_ORDER} for g in geoms]
+        want = [{n: torch.from_numpy(f[n].copy()).view(rows(g, n), pitch[n]) for n in FIELD_ORDER} for g, f in zip(geoms, flat)]
+        local_exchange(geoms, [[(w_[n], "u" if n == "u" else "c") for n in FIELD_ORDER] for w_ in want])
+        for r in range(world):                                                                # push
+            for side, link in links[r].items():
+                peer = r - 1 if side == 0 else r + 1
+                for f, n in enumerate(FIELD_ORDER):
+                    so, sc, _, _ = link[n]
+                    assert sc <= field_stride and so % 4 == 0 and sc % 4 == 0
+                    mail[peer][1 - side, seq & 1, f, :sc] = flat[r][n][so:so + sc]
+        for r in range(world):                                                                # unpack
+            for side, link in links[r].items():
+                for f, n in enumerate(FIELD_ORDER):
+                    _, _, ro, rc = link[n]
+                    flat[r][n][ro:ro + rc] = mail[r][side, seq & 1, f, :rc]
+        for r, g in enumerate(geoms):
+            for n in FIELD_ORDER:
+                assert np.array_equal(flat[r][n].reshape(rows(g, n), pitch[n]), want[r][n].numpy()), (seq, r, n)
