@@ -319,10 +319,13 @@ static int pick_step_kernel(const smk_grid_t* g, const smk_params_t* prm, int ns
         // calls), 8 simulations equal, 32 simulations 38.7 against 30.0; single-step calls 39.8 against 45.3 at 32 simulations.
         // 96 x 96 (generic fused kernel): 32 simulations 36.8 against 47.8, 148 simulations 77 against 63.  Below 96 x 96
         // the phase path always wins (64 x 64: 52 against 65 us per step of 148 simulations).
-        const bool full = g->h == 128 && g->w == 128;
+        // Round 2: a few full-size simulations (up to 33) run on clusters of four CTAs (k_step_cluster): 27.3 us per step at K = 40 for
+        // 1 .. 32 simulations against 36.6 .. 48.4 on the phase path (tools/cluster_latency.py), so those take the fused path too.
+        const bool full = g->h == 128 && g->w == 128 && g->pitch_u == 128 && g->pitch_v == 132 && g->pitch_c == 128;
         const bool big_enough = (long)g->h * g->w >= 96L * 96L;
         const int need = full ? (nsteps >= 2 ? 12 : 48) : 96;
-        *fused = (prm->step_kernel == SMK_STEP_FUSED || (big_enough && g->batch >= need)) ? 1 : 0;
+        const bool clustered = full && pick_cluster(g->batch) != 0;
+        *fused = (prm->step_kernel == SMK_STEP_FUSED || clustered || (big_enough && g->batch >= need)) ? 1 : 0;
         return SMK_OK;
     }
     if (prm->step_kernel == SMK_STEP_FUSED)

@@ -133,6 +133,7 @@ int launch_frame_features(const float* frames, int64_t frame_stride, int nframes
                           const float* edges, int nbins, float lo, float hi, int* box_counts, int* hist, float* mean_out, cudaStream_t s);
 int launch_frame_distances(const float* frames, int64_t frame_stride, int nframes, int h, int w, int pitch, double* sumsq, cudaStream_t s);
 bool fused_supported(const smk_grid_t* g);
+int pick_cluster(int batch);          // CTAs per simulation k_step_cluster would use for `batch` 128 x 128 simulations (0: one CTA each)
 int launch_steps_fused(const smk_grid_t* g, float* u, float* v, float* d, float* p, int nsteps, float* frames,
                        int64_t frame_step_stride, int64_t frame_batch_stride, const float* fmul,
                        float dt, float c_uv, float c_d, float decay, int K, float* scratch, cudaStream_t s);

@@ -657,15 +657,76 @@ k_step_fused(const FusedArgs a)
 constexpr int CH = 2;                                   // halo rows kept on either side of a CTA's band
 
 template <int NC> struct ClusterCfg {
-    static constexpr int RB = 128 / NC, NW = RB / 8, NT = NW * 32;
+    // 16 warps per CTA whatever the split: a warp owns R = 8 / NC rows (lane = 4 columns), a thread 4 R cells.  (A first version
+    // kept k_step_fused's 8 rows per warp, i.e. 16 / NC warps per CTA: one warp per scheduler cannot hide the shared-memory and
+    // FP latencies of this code, and four SMs ran a simulation SLOWER than one -- 49 against 40 us per step.)
+    static constexpr int RB = 128 / NC, NW = 16, NT = NW * 32, R = RB / NW;
     static constexpr int SU_ROWS = RB + 2 * CH + 1, SV_ROWS = RB + 2 * CH, SD_ROWS = RB + 2 * CH;
     static constexpr int SU = SU_ROWS * FZ_PU, SV = SV_ROWS * FZ_PV, SD = SD_ROWS * FZ_PD;       // floats
-    static constexpr size_t SMEM = (size_t)(SU + SV + SD) * 4 + sizeof(float4) * (2 * 2 * NW * 32 + 2 * 2 * 32);
+    static constexpr size_t SMEM = (size_t)(SU + SV + SD) * 4 + sizeof(float4) * (2 * 2 * NW * 32 + 2 * 2 * 32) + 4 * sizeof(unsigned long long);
 };
+
+// zdiffuse_strip for a strip of R rows
+template <int PITCH, int R>
+__device__ __forceinline__ void cdiffuse_strip(const float* F, const int rows, const int cols, const float c, float4 (&out)[R],
+                                               const int r0, const int c0, const int lane)
+{
+    const int rlast = rows - 1, clast = cols - 1;
+    float4 up = zlds4(F + min(max(r0 - 1, 0), rlast) * PITCH + c0);
+    float4 cur = zlds4(F + min(r0, rlast) * PITCH + c0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = r0 + r;
+        const float4 dn = zlds4(F + min(i + 1, rlast) * PITCH + c0);
+        float left = __shfl_up_sync(0xffffffffu, cur.w, 1);
+        float right = __shfl_down_sync(0xffffffffu, cur.x, 1);
+        if (lane == 0) left = cur.x;
+        if (lane == 31 && clast >= 128) right = F[min(i, rlast) * PITCH + 128];       // the staggered column of v
+        out[r].x = zdiff1(cur.x, up.x, dn.x, left, (c0 + 1 <= clast) ? cur.y : cur.x, c);
+        out[r].y = zdiff1(cur.y, up.y, dn.y, cur.x, (c0 + 2 <= clast) ? cur.z : cur.y, c);
+        out[r].z = zdiff1(cur.z, up.z, dn.z, cur.y, (c0 + 3 <= clast) ? cur.w : cur.z, c);
+        out[r].w = zdiff1(cur.w, up.w, dn.w, cur.z, (c0 + 4 <= clast) ? right : cur.w, c);
+        up = cur; cur = dn;
+    }
+}
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
+// Execution barrier only (no release fence: ptxas implements the cluster-scope release as MEMBAR.ALL.GPU, ~0.7 us here): for
+// the "everybody has finished READING the old values" points, where no data has to become visible.
+__device__ __forceinline__ void cluster_sync_exec()
+{
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned csmem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// shared::cluster address of the same location in CTA `rank`
+__device__ __forceinline__ unsigned cluster_map32(const unsigned local, const unsigned rank)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+// 16 bytes into another CTA's shared memory; the store itself signals the destination mbarrier (complete_tx 16 bytes): no fence,
+// no separate arrive -- data and signal travel together (STAS.128)
+__device__ __forceinline__ void st_async_f4(const unsigned remote_data, const float4 v, const unsigned remote_mbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 :: "r"(remote_data), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)),
+                    "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void cmbar_wait(const unsigned bar, const unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cmbar_arm(const unsigned bar, const unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ unsigned cluster_rank()
 {
     unsigned r;
@@ -761,7 +822,7 @@ __global__ void __launch_bounds__(ClusterCfg<NC>::NT, 1)
 k_step_cluster(const FusedArgs a)
 {
     typedef ClusterCfg<NC> C;
-    constexpr int RB = C::RB, NW = C::NW, NT = C::NT;
+    constexpr int RB = C::RB, NW = C::NW, NT = C::NT, R = C::R;
     constexpr int h = 128, w = 128, pu = 128, pv = 132, pc = 128;
     extern __shared__ __align__(16) float smem[];
     float* su_s = smem;                       // storage: row 0 of each array is global row g0 = c RB - CH
@@ -769,12 +830,13 @@ k_step_cluster(const FusedArgs a)
     float* sd_s = sv_s + C::SV;
     float4 (*halo)[2][NW][32] = reinterpret_cast<float4 (*)[2][NW][32]>(sd_s + C::SD);
     float4 (*xp)[2][32] = reinterpret_cast<float4 (*)[2][32]>(reinterpret_cast<float4*>(sd_s + C::SD) + 2 * 2 * NW * 32);   // [parity][0: from above, 1: from below]
+    unsigned long long* mb = reinterpret_cast<unsigned long long*>(reinterpret_cast<float4*>(sd_s + C::SD) + 2 * 2 * NW * 32 + 2 * 2 * 32);   // mb[parity * 2 + side]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = (int)cluster_rank();
     const size_t b = blockIdx.x / NC;
     const int g0 = c * RB - CH;               // first stored row (may be negative: rows outside the grid are never touched)
-    const int r0 = c * RB + warp * FZ_R, c0 = lane * 4;
+    const int r0 = c * RB + warp * R, c0 = lane * 4;
     const bool last_cta = c == NC - 1;
     float* __restrict__ gU = a.U + b * a.su_;
     float* __restrict__ gV = a.V + b * a.sv_;
@@ -782,6 +844,12 @@ k_step_cluster(const FusedArgs a)
     float* __restrict__ gP = a.P + b * a.sc_;
     const float dt = a.dt;
     const FzDiv fzdiv = zdiv_setup(dt);
+#ifdef SMK_FUSED_TIMING
+    long long tick0_ = clock64();
+#define CL_TICK(k) do { if (tid == 0 && blockIdx.x == 0) { const long long t1_ = clock64(); a.ticks[k] += t1_ - tick0_; tick0_ = t1_; } } while (0)
+#else
+#define CL_TICK(k) do { } while (0)
+#endif
 
     CField fu, fv, fd;
     fu.mine = su_s - g0 * FZ_PU; fv.mine = sv_s - g0 * FZ_PV; fd.mine = sd_s - g0 * FZ_PD;
@@ -798,17 +866,31 @@ k_step_cluster(const FusedArgs a)
     fv.last = fd.last = c * RB + RB - 1;
     fu.last = last_cta ? 128 : c * RB + RB - 1;
     float* const su = fu.mine; float* const sv = fv.mine; float* const sd = fd.mine;
-    float4 (*xp_up)[2][32] = c > 0 ? cluster_map(xp, c - 1) : nullptr;
-    float4 (*xp_dn)[2][32] = !last_cta ? cluster_map(xp, c + 1) : nullptr;
+    // Jacobi boundary rows between CTAs: this CTA's first row goes to the upper neighbour's xp[parity][1][lane] and signals its
+    // mb[parity][1]; the last row goes to the lower neighbour's xp[parity][0][lane] / mb[parity][0] (st.async: data + signal)
+    const bool has_up = c > 0, has_dn = !last_cta;
+    const unsigned rxp_up = has_up ? cluster_map32(csmem(&xp[0][1][lane]), c - 1) : 0u, rmb_up = has_up ? cluster_map32(csmem(&mb[1]), c - 1) : 0u;
+    const unsigned rxp_dn = has_dn ? cluster_map32(csmem(&xp[0][0][lane]), c + 1) : 0u, rmb_dn = has_dn ? cluster_map32(csmem(&mb[0]), c + 1) : 0u;
+    constexpr unsigned XP_PAR = 2 * 32 * sizeof(float4), MB_PAR = 2 * sizeof(unsigned long long);      // byte distance of the parity-1 copies
+    const unsigned mb_local = csmem(mb);
+    unsigned phase = 0;                       // bit (parity * 2 + side): the phase parity this thread waits for next on mb[parity][side]
+    if (tid == 0) {
+        for (int k = 0; k < 4; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb_local + 8u * k) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // a row is 32 lanes x 16 bytes; every barrier is armed for its first use here and re-armed by its consumer after each use
+        for (int k = 0; k < 4; ++k)
+            if ((k & 1) ? has_dn : has_up) cmbar_arm(mb_local + 8u * k, 512u);
+    }
     // rows of the stored windows that exist in the grid
     const int slo = max(g0, 0);
-    const int shi_u = min(g0 + C::SU_ROWS - 1, 128), shi_c = min(g0 + C::SV_ROWS - 1, 127);
-    // u's staggered row 128 is owned by the last CTA: its 128 columns are spread over the lanes of that CTA
-    constexpr int XL = 128 / NW;              // lanes per warp that carry one extra cell
-    const int xe = XL * warp + lane;
-    const bool xu = last_cta && lane < XL;
-    // v's staggered column 128: one cell per owned row, lanes 0..7 of the warp that owns the row
-    const bool xv = lane < 8;
+    // (u keeps one more storage row than the CH halo rows below the band -- it is row 128 for the last CTA -- but only the halo
+    //  rows are refreshed by the neighbour: the row after them is stale and must not be gathered from)
+    const int shi_u = last_cta ? 128 : c * RB + RB + CH - 1, shi_c = min(g0 + C::SV_ROWS - 1, 127);
+    // u's staggered row 128 is owned by the last CTA: its 128 columns are spread over lanes 0..7 of that CTA's 16 warps
+    const int xe = 8 * warp + lane;
+    const bool xu = last_cta && lane < 8;
+    // v's staggered column 128: one cell per owned row, lanes 0..R-1 of the warp that owns the row
+    const bool xv = lane < R;
     const int xr = r0 + lane;
 
     // ---- load: stored rows of u, v, density (own rows and the halo rows, all straight from global memory), own pressure rows
@@ -824,28 +906,20 @@ k_step_cluster(const FusedArgs a)
         const int i = slo + k / (pc / 4), g = k % (pc / 4);
         zsts4(sd + i * FZ_PD + 4 * g, __ldcg(reinterpret_cast<const float4*>(gD + (size_t)i * pc + 4 * g)));
     }
-    FzStrip P = {};
-    unsigned ringmask = 0;
+    float4 P[R];
 #pragma unroll
-    for (int r = 0; r < FZ_R; ++r) {
-        const int i = r0 + r;
-        packed_set_row(P, r, __ldcg(reinterpret_cast<const float4*>(gP + (size_t)i * pc + c0)));
-        if (i < 1 || i > h - 2) ringmask |= 1u << r;
-    }
-    FzElem M[4];
+    for (int r = 0; r < R; ++r) P[r] = __ldcg(reinterpret_cast<const float4*>(gP + (size_t)(r0 + r) * pc + c0));
+    float cm[4];                              // 0.25 inside, 0 on the Dirichlet ring columns
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-        const float m = (c0 + cc >= 1 && c0 + cc <= w - 2) ? 0.25f : 0.f;
-        M[cc] = pe_make<FzElem>(make_float2(m, m));
-    }
+    for (int cc = 0; cc < 4; ++cc) cm[cc] = (c0 + cc >= 1 && c0 + cc <= w - 2) ? 0.25f : 0.f;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     // buoyancy (:154-155) on the owned rows of v and, redundantly, on the stored halo rows (they stay current without an exchange);
     // the frame of the step just finished comes from the owned rows of density
-    auto frame_and_buoyancy = [&](float* frame, const bool buoy, const float4 (&mrow)[FZ_R]) {
+    auto frame_and_buoyancy = [&](float* frame, const bool buoy, const float4 (&mrow)[R]) {
 #pragma unroll
-        for (int r = 0; r < FZ_R; ++r) {
+        for (int r = 0; r < R; ++r) {
             const int i = r0 + r;
             const float4 d4 = zlds4(sd + i * FZ_PD + c0);
             if (frame) {
@@ -876,10 +950,11 @@ k_step_cluster(const FusedArgs a)
         }
     };
     {
-        const float4 none[FZ_R] = {};
+        const float4 none[R] = {};
         frame_and_buoyancy(nullptr, true, none);
     }
     cluster_sync_all();          // every CTA of the cluster is past its loads before anybody stores into a neighbour
+    CL_TICK(0);
 
     // gathers of back-traces that leave the stored rows: from the owner CTA's shared memory (its OWN rows are current)
     auto far_u = [&](const int y, const int x) { const int rk = min(y / RB, NC - 1); return cluster_map(su_s, rk)[(y - (rk * RB - CH)) * FZ_PU + x]; };
@@ -889,33 +964,34 @@ k_step_cluster(const FusedArgs a)
     for (int t = 0; t < a.nsteps; ++t) {
         // ---- a4 diffusion of u, v, density: strip mapping, halo rows give the rows above / below the band          :158-160
         {
-            float4 R[FZ_R];
+            float4 Rs[R];
             float X = 0.f;
-            zdiffuse_strip<FZ_PU>(su, h + 1, w, a.c_uv, R, r0, c0, lane);
+            cdiffuse_strip<FZ_PU, R>(su, h + 1, w, a.c_uv, Rs, r0, c0, lane);
             if (xu) X = zdiff_cell(su, FZ_PU, h + 1, w, 128, xe, a.c_uv);
-            cluster_sync_all();                       // everybody has read the old u (own rows and halo copies)
+            cluster_sync_exec();                       // everybody has read the old u (own rows and halo copies)
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r) cput4<FZ_PU>(fu, r0 + r, c0, R[r]);
+            for (int r = 0; r < R; ++r) cput4<FZ_PU>(fu, r0 + r, c0, Rs[r]);
             if (xu) su[128 * FZ_PU + xe] = X;
-            zdiffuse_strip<FZ_PV>(sv, h, w + 1, a.c_uv, R, r0, c0, lane);
+            cdiffuse_strip<FZ_PV, R>(sv, h, w + 1, a.c_uv, Rs, r0, c0, lane);
             if (xv) X = zdiff_cell(sv, FZ_PV, h, w + 1, xr, 128, a.c_uv);
-            cluster_sync_all();
+            cluster_sync_exec();
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r) cput4<FZ_PV>(fv, r0 + r, c0, R[r]);
+            for (int r = 0; r < R; ++r) cput4<FZ_PV>(fv, r0 + r, c0, Rs[r]);
             if (xv) cput1<FZ_PV>(fv, xr, 128, X);
-            zdiffuse_strip<FZ_PD>(sd, h, w, a.c_d, R, r0, c0, lane);
-            cluster_sync_all();
+            cdiffuse_strip<FZ_PD, R>(sd, h, w, a.c_d, Rs, r0, c0, lane);
+            cluster_sync_exec();
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r) cput4<FZ_PD>(fd, r0 + r, c0, R[r]);
+            for (int r = 0; r < R; ++r) cput4<FZ_PD>(fd, r0 + r, c0, Rs[r]);
             cluster_sync_all();                       // the new rows and halo rows are visible
         }
+        CL_TICK(1);
 
         // ---- a5 divergence into registers                                                                          :136
-        FzStrip ND = {};
+        float4 Dv[R];
         {
             float4 ua = zlds4(su + r0 * FZ_PU + c0);
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r) {
+            for (int r = 0; r < R; ++r) {
                 const int i = r0 + r;
                 const float4 ub = zlds4(su + (i + 1) * FZ_PU + c0);
                 const float4 va = zlds4(sv + i * FZ_PV + c0);
@@ -925,60 +1001,83 @@ k_step_cluster(const FusedArgs a)
                 o.y = ((ub.y - ua.y) + va.z) - va.y;
                 o.z = ((ub.z - ua.z) + va.w) - va.z;
                 o.w = ((ub.w - ua.w) + vr) - va.w;
-                o = zdiv4(o, fzdiv);
-                packed_set_row(ND, r, make_float4(-o.x, -o.y, -o.z, -o.w));
+                Dv[r] = zdiv4(o, fzdiv);
                 ua = ub;
             }
         }
 
-        // ---- a6 K Jacobi sweeps: boundary rows first, posted to the neighbouring warps (shared memory) and CTAs (DSMEM),
-        //      cluster barrier arrive, interior rows, cluster barrier wait                                          :139-145
-        halo[0][0][warp][lane] = packed_row(P, 0);
-        halo[0][1][warp][lane] = packed_row(P, 7);
-        if (warp == 0 && xp_up) xp_up[0][1][lane] = packed_row(P, 0);
-        if (warp == NW - 1 && xp_dn) xp_dn[0][0][lane] = packed_row(P, 7);
-        cluster_sync_all();
-        {
-            FzStrip Q;
-            auto sweep = [&](const FzStrip& S, FzStrip& Dst, const int q) {
-                const float4 up = warp > 0 ? halo[q][1][warp - 1][lane] : (c > 0 ? xp[q][0][lane] : zero4);
-                const float4 dn = warp < NW - 1 ? halo[q][0][warp + 1][lane] : (!last_cta ? xp[q][1][lane] : zero4);
-                packed_pair<0, (FZ_PMASK & 1) != 0>(S, Dst, ND, up, dn, M);
-                packed_pair<3, (FZ_PMASK & 8) != 0>(S, Dst, ND, up, dn, M);
-                if (ringmask & 0x81u) {
-                    if (ringmask & 1u) packed_set_row(Dst, 0, zero4);
-                    if (ringmask & 0x80u) packed_set_row(Dst, 7, zero4);
-                }
-                const float4 n0 = packed_row(Dst, 0), n7 = packed_row(Dst, 7);
-                halo[q ^ 1][0][warp][lane] = n0;
-                halo[q ^ 1][1][warp][lane] = n7;
-                if (warp == 0 && xp_up) xp_up[q ^ 1][1][lane] = n0;
-                if (warp == NW - 1 && xp_dn) xp_dn[q ^ 1][0][lane] = n7;
-                cluster_arrive();
-                packed_pair<1, (FZ_PMASK & 2) != 0>(S, Dst, ND, up, dn, M);
-                packed_pair<2, (FZ_PMASK & 4) != 0>(S, Dst, ND, up, dn, M);
-                if (ringmask & 0x7eu) packed_zero_rows(Dst, ringmask & 0x7eu);
-                cluster_wait();
-            };
-            int s = 0;
-            for (; s + 1 < a.K; s += 2) {
-                sweep(P, Q, 0);
-                sweep(Q, P, 1);
+        CL_TICK(2);
+        // ---- a6 K Jacobi sweeps.  A warp's boundary rows are computed first and posted at once: to the neighbouring warps through
+        //      shared memory (published by the CTA barrier at the end of the sweep), to the neighbouring CTA by st.async, which
+        //      signals that CTA's mbarrier by itself.  Only the two warps at the ends of the band ever wait for another CTA, at
+        //      the start of the next sweep, by when the row has had a whole sweep to arrive.  No cluster barrier in the loop.
+        //      Two copies (sweep parity) of every line: a line is rewritten two sweeps after it was read, and its writer cannot
+        //      be two sweeps ahead of its reader (it needs the reader's row of the sweep in between).                :139-145
+        auto post = [&](const int q, const float4 first, const float4 last) {       // lines that sweeps of parity q read
+            halo[q][0][warp][lane] = first;
+            halo[q][1][warp][lane] = last;
+            if (warp == 0 && has_up) st_async_f4(rxp_up + q * XP_PAR, first, rmb_up + q * MB_PAR);
+            if (warp == NW - 1 && has_dn) st_async_f4(rxp_dn + q * XP_PAR, last, rmb_dn + q * MB_PAR);
+        };
+        auto from_above = [&](const int q) -> float4 {                              // row above this warp's strip, parity q
+            if (warp > 0) return halo[q][1][warp - 1][lane];
+            if (!has_up) return zero4;
+            const unsigned bit = 1u << (q * 2);
+            cmbar_wait(mb_local + 8u * (q * 2), (phase & bit) ? 1u : 0u);
+            phase ^= bit;
+            const float4 v = xp[q][0][lane];
+            __syncwarp();
+            if (lane == 0) cmbar_arm(mb_local + 8u * (q * 2), 512u);
+            return v;
+        };
+        auto from_below = [&](const int q) -> float4 {
+            if (warp < NW - 1) return halo[q][0][warp + 1][lane];
+            if (!has_dn) return zero4;
+            const unsigned bit = 1u << (q * 2 + 1);
+            cmbar_wait(mb_local + 8u * (q * 2 + 1), (phase & bit) ? 1u : 0u);
+            phase ^= bit;
+            const float4 v = xp[q][1][lane];
+            __syncwarp();
+            if (lane == 0) cmbar_arm(mb_local + 8u * (q * 2 + 1), 512u);
+            return v;
+        };
+        post(0, P[0], P[R - 1]);
+        __syncthreads();
+        for (int s = 0; s < a.K; ++s) {
+            const int q = s & 1;
+            const float4 up = from_above(q), dn = from_below(q);
+            // boundary rows first (for R <= 2 every row is one), posted at once; then the rows in between.  Row r is on the ring (and
+            // stays zero) when its global index is 0 or 127: the mask multiplies by 0 instead of 0.25, like every other Jacobi kernel here.
+            const bool ok0 = r0 >= 1 && r0 <= h - 2, okL = r0 + R - 1 >= 1 && r0 + R - 1 <= h - 2;
+            const float4 o0 = P[0], oL = P[R - 1];
+            const float4 n0 = stencil_row(up, o0, R > 1 ? P[1] : dn, Dv[0], ok0 ? cm[0] : 0.f, ok0 ? cm[1] : 0.f, ok0 ? cm[2] : 0.f, ok0 ? cm[3] : 0.f);
+            const float4 nL = R > 1 ? stencil_row(P[R - 2], oL, dn, Dv[R - 1], okL ? cm[0] : 0.f, okL ? cm[1] : 0.f, okL ? cm[2] : 0.f, okL ? cm[3] : 0.f) : n0;
+            post(q ^ 1, n0, nL);
+            float4 prev = o0;
+#pragma unroll
+            for (int r = 1; r < R - 1; ++r) {                                      // interior rows are never ring rows (R divides the band)
+                const float4 cur = P[r];
+                const float4 below = (r < R - 2) ? P[r + 1] : oL;
+                P[r] = stencil_row(prev, cur, below, Dv[r], cm[0], cm[1], cm[2], cm[3]);
+                prev = cur;
             }
-            if (s < a.K) {
-                sweep(P, Q, 0);
-                P = Q;
-            }
+            P[0] = n0;
+            if (R > 1) P[R - 1] = nL;
+            __syncthreads();
         }
 
+        CL_TICK(3);
         // ---- a7 gradient subtract on the owned rows, then the neighbours' halo rows of u and v                   :148-149
         {
+            // the lines posted by the last sweep (parity K & 1): the row above comes from them; the row below is not needed here, but
+            // the line from the CTA below has to be consumed so that its mbarrier stays in step with the sweeps of the next step
             const int q = a.K & 1;
-            float4 pabove = warp > 0 ? halo[q][1][warp - 1][lane] : (c > 0 ? xp[q][0][lane] : zero4);
+            float4 pabove = from_above(q);
+            if (warp == NW - 1 && has_dn) (void)from_below(q);
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r) {
+            for (int r = 0; r < R; ++r) {
                 const int i = r0 + r;
-                const float4 pc4 = packed_row(P, r);
+                const float4 pc4 = P[r];
                 const float pleft = __shfl_up_sync(0xffffffffu, pc4.w, 1);
                 float4 u4 = zlds4(su + i * FZ_PU + c0);
                 float4 v4 = zlds4(sv + i * FZ_PV + c0);
@@ -995,80 +1094,83 @@ k_step_cluster(const FusedArgs a)
         }
         cluster_sync_all();
 
-        float4 mrow[FZ_R] = {};
+        CL_TICK(4);
+        float4 mrow[R] = {};
         // ---- a10/a11 advection (cyclic mapping): u by (u, v); v by (u', v); density by (u', v'), decay              :166-171
         {
-            float2 R[FZ_R][2];
+            float2 Ra[R][2];
             float X = 0.f;
             const float ulo = (float)slo, uhi = (float)shi_u, chi = (float)shi_c;
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r)
+            for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int kp = 0; kp < 2; ++kp)
-                    R[r][kp] = cadvect_pair<FZ_PU, false, NC>(su, h + 1, w, su, sv, r0 + r, lane + 64 * kp, dt, 1.0f, ulo, uhi, far_u);
+                    Ra[r][kp] = cadvect_pair<FZ_PU, false, NC>(su, h + 1, w, su, sv, r0 + r, lane + 64 * kp, dt, 1.0f, ulo, uhi, far_u);
             if (xu) X = zadvect_cell<FZ_PU>(su, h + 1, w, su, sv, h, w, 128, xe, dt);       // row 128 back-traces to itself (zero velocity there)
-            cluster_sync_all();                       // every gather of the cluster (near and far) is done
+            cluster_sync_exec();                       // every gather of the cluster (near and far) is done
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r)
+            for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int kp = 0; kp < 2; ++kp) {
                     const int i = r0 + r, j = lane + 64 * kp;
-                    cput1<FZ_PU>(fu, i, j, R[r][kp].x);
-                    cput1<FZ_PU>(fu, i, j + 32, R[r][kp].y);
+                    cput1<FZ_PU>(fu, i, j, Ra[r][kp].x);
+                    cput1<FZ_PU>(fu, i, j + 32, Ra[r][kp].y);
                 }
             if (xu) su[128 * FZ_PU + xe] = X;
             cluster_sync_all();
 
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r)
+            for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int kp = 0; kp < 2; ++kp)
-                    R[r][kp] = cadvect_pair<FZ_PV, false, NC>(sv, h, w + 1, su, sv, r0 + r, lane + 64 * kp, dt, 1.0f, ulo, chi, far_v);
+                    Ra[r][kp] = cadvect_pair<FZ_PV, false, NC>(sv, h, w + 1, su, sv, r0 + r, lane + 64 * kp, dt, 1.0f, ulo, chi, far_v);
             // the staggered column 128 of v: both interpolated velocities are zero there (navier_stokes.py:97-109), so the cell
             // back-traces to itself and only touches its own row
             if (xv) X = zadvect_cell<FZ_PV>(sv, h, w + 1, su, sv, h, w, xr, 128, dt);
-            cluster_sync_all();
+            cluster_sync_exec();
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r)
+            for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int kp = 0; kp < 2; ++kp) {
                     const int i = r0 + r, j = lane + 64 * kp;
-                    cput1<FZ_PV>(fv, i, j, R[r][kp].x);
-                    cput1<FZ_PV>(fv, i, j + 32, R[r][kp].y);
+                    cput1<FZ_PV>(fv, i, j, Ra[r][kp].x);
+                    cput1<FZ_PV>(fv, i, j + 32, Ra[r][kp].y);
                 }
             if (xv) cput1<FZ_PV>(fv, xr, 128, X);
             cluster_sync_all();
 
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r)
+            for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int kp = 0; kp < 2; ++kp)
-                    R[r][kp] = cadvect_pair<FZ_PD, true, NC>(sd, h, w, su, sv, r0 + r, lane + 64 * kp, dt, a.decay, ulo, chi, far_d);
-            cluster_sync_all();
+                    Ra[r][kp] = cadvect_pair<FZ_PD, true, NC>(sd, h, w, su, sv, r0 + r, lane + 64 * kp, dt, a.decay, ulo, chi, far_d);
+            cluster_sync_exec();
             if (a.frames && a.fmul) {
 #pragma unroll
-                for (int r = 0; r < FZ_R; ++r) mrow[r] = __ldg(reinterpret_cast<const float4*>(a.fmul + (size_t)(r0 + r) * pc + c0));
+                for (int r = 0; r < R; ++r) mrow[r] = __ldg(reinterpret_cast<const float4*>(a.fmul + (size_t)(r0 + r) * pc + c0));
             }
 #pragma unroll
-            for (int r = 0; r < FZ_R; ++r)
+            for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int kp = 0; kp < 2; ++kp) {
                     const int i = r0 + r, j = lane + 64 * kp;
-                    cput1<FZ_PD>(fd, i, j, R[r][kp].x);
-                    cput1<FZ_PD>(fd, i, j + 32, R[r][kp].y);
+                    cput1<FZ_PD>(fd, i, j, Ra[r][kp].x);
+                    cput1<FZ_PD>(fd, i, j + 32, Ra[r][kp].y);
                 }
             cluster_sync_all();
         }
 
+        CL_TICK(5);
         // ---- a11 returned copy of this step + buoyancy of the next
         float* frame = a.frames ? a.frames + b * a.frame_batch_stride + (size_t)t * a.frame_step_stride : nullptr;
         frame_and_buoyancy(frame, t + 1 < a.nsteps, mrow);
         __syncthreads();
+        CL_TICK(6);
     }
 
     // ---- write back the owned rows: pressure from registers, u, v, density from shared memory ------------------------------
 #pragma unroll
-    for (int r = 0; r < FZ_R; ++r) *reinterpret_cast<float4*>(gP + (size_t)(r0 + r) * pc + c0) = packed_row(P, r);
+    for (int r = 0; r < R; ++r) *reinterpret_cast<float4*>(gP + (size_t)(r0 + r) * pc + c0) = P[r];
     {
         const int first = c * RB;
         for (int k = tid; k < (fu.last - first + 1) * (pu / 4); k += NT) {
@@ -1085,6 +1187,8 @@ k_step_cluster(const FusedArgs a)
         }
     }
     cluster_sync_all();          // no CTA leaves (and frees its shared memory) while a neighbour may still read or write it
+    CL_TICK(7);
+#undef CL_TICK
 }
 
 // does the current device give one CTA the 226.5 KB the fused kernel needs (B200: 227 KB)?
@@ -1163,17 +1267,18 @@ int fused_plan(int nsims, int nsteps, int piece_len, int32_t* items, int capacit
 }
 
 // CTAs per simulation for a call of `batch` full-size (128 x 128) simulations: 0 = one CTA per simulation (k_step_fused), 2 or 4 =
-// k_step_cluster.  A cluster pays when the simulations would leave most SMs idle: up to 33 simulations fit four CTAs each (the
-// hardware co-schedules 33 clusters of 4 on the 148 SMs of a B200), up to 74 two each.  SMK_FUSED_CLUSTER = 0 / 2 / 4 forces.
-static int pick_cluster(const int batch)
+// k_step_cluster.  SMK_FUSED_CLUSTER = 0 / 2 / 4 forces.
+int pick_cluster(const int batch)
 {
     int nsm = 0, dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) return 0;
     const int forced = env().fused_cluster;
     if (forced != SMK_ENV_UNSET) return (forced == 2 || forced == 4) ? forced : 0;
-    if (batch * 4 <= (nsm / 4 - 4) * 4) return 4;         // 148 SMs: 33 clusters of four
-    if (batch * 2 <= nsm) return 2;
-    return 0;
+    // Measured (tools/cluster_latency.py, K = 40, us per step of a 20-step call): one CTA per simulation 39.7 at any batch up to 148;
+    // clusters of four 27.3 - 28.3 up to 32 simulations, 55 from 48 on (a B200 co-schedules 33 clusters of four: a second wave);
+    // clusters of two 41.2: no gain, because a sweep's critical path is the round trip of a boundary row between two SMs, not
+    // the arithmetic.  So: four CTAs per simulation while all clusters are co-resident, else one.
+    return (batch <= nsm / 4 - 4) ? 4 : 0;
 }
 
 template <int NC>

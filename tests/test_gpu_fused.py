@@ -40,12 +40,16 @@ def random_state(h, w, seed, vel=300.0):
 
 
 def test_dispatch_rules():
-    """auto: the one-simulation-per-SM kernel needs enough simulations to fill SMs -- 12 for a multi-step call on 128 x 128,
-    48 for a single step, 96 on smaller grids from 96 x 96; fewer run on the phase kernels spread over all SMs."""
-    assert not make(128, 128).step_is_fused()               # one step of one simulation: phase kernels over all SMs
-    assert not make(128, 128).step_is_fused(nsteps=20) and not make(128, 128, batch=8).step_is_fused(nsteps=20)
-    assert make(128, 128, batch=12).step_is_fused(nsteps=2) and not make(128, 128, batch=12).step_is_fused()
-    assert make(128, 128, batch=48).step_is_fused() and not make(128, 128, batch=32).step_is_fused()
+    """auto on 128 x 128: up to 33 simulations run on clusters of four CTAs each (k_step_cluster) whatever the call; more than
+    that need enough simulations for one-simulation-per-SM execution to win -- 12 for a multi-step call, 48 for a single step;
+    smaller grids from 96 x 96 need 96; everything else runs on the phase kernels spread over all SMs."""
+    assert make(128, 128).step_is_fused() and make(128, 128).step_is_fused(nsteps=20)       # one simulation: a cluster of four SMs
+    assert make(128, 128, batch=8).step_is_fused(nsteps=20) and make(128, 128, batch=33).step_is_fused()
+    assert make(128, 128, batch=34).step_is_fused(nsteps=2) and not make(128, 128, batch=34).step_is_fused()
+    assert make(128, 128, batch=48).step_is_fused() and not make(128, 128, batch=47).step_is_fused()
+    with smk_env(SMK_FUSED_CLUSTER=0):                     # without the cluster kernel: the round-1 rules
+        assert not make(128, 128).step_is_fused() and not make(128, 128, batch=8).step_is_fused(nsteps=20)
+        assert make(128, 128, batch=12).step_is_fused(nsteps=2) and not make(128, 128, batch=32).step_is_fused()
     assert not make(96, 40, batch=256).step_is_fused(20) and not make(96, 96, batch=32).step_is_fused(20)
     assert make(96, 96, batch=96).step_is_fused(20) and make(100, 120, batch=148).step_is_fused()
     assert not make(100, 120, batch=3).step_is_fused()
@@ -58,12 +62,15 @@ def test_dispatch_rules():
     with pytest.raises(ValueError):
         make(64, 64, step_kernel="tensor-cores")
     # the dispatch is observable in the launch count: 6 phase kernels per step against 1 fused launch per call
-    ns = make(128, 128)
+    ns = make(100, 128)
     n0 = _lib.launch_count(); ns.step(); n1 = _lib.launch_count(); ns.run_steps(3); n2 = _lib.launch_count()
     assert (n1 - n0, n2 - n1) == (6, 18)
-    ns = make(128, 128, batch=16)
+    ns = make(128, 128, batch=40)
     n0 = _lib.launch_count(); ns.step(); n1 = _lib.launch_count(); ns.run_steps(3); n2 = _lib.launch_count()
     assert (n1 - n0, n2 - n1) == (6, 1)
+    ns = make(128, 128, batch=16)
+    n0 = _lib.launch_count(); ns.step(); n1 = _lib.launch_count(); ns.run_steps(3); n2 = _lib.launch_count()
+    assert (n1 - n0, n2 - n1) == (1, 1)
 
 
 @pytest.mark.parametrize("h,w,K", [
