@@ -72,7 +72,7 @@ def phase_bytes_per_cell(K, sweeps_in_launch, steps_in_launch=1):
         "project_advect_u": 20 + 12,        # k_project_advect_u: gradient subtract and the u advection in one kernel
         "advect_d": 16 + 4,                 # R(u,v,d) W(d) + the returned copy
         "splat": 8,
-        "other": 0, "halo": 0,
+        "other": 0, "halo": 0, "halo_unpack": 0,
     }
 
 
@@ -83,13 +83,13 @@ def phase_flops_per_cell(K, sweeps_in_launch, steps_in_launch=1):
     return {
         "step_fused": (118 + 5 * K) * steps_in_launch,
         "forces_diffuse_div": 3 + 21 + 4, "jacobi": 5 * sweeps_in_launch, "project": 6,
-        "advect_u": 27, "advect_v": 27, "project_advect_u": 33, "advect_d": 30, "splat": 0, "other": 0, "halo": 0,
+        "advect_u": 27, "advect_v": 27, "project_advect_u": 33, "advect_d": 30, "splat": 0, "other": 0, "halo": 0, "halo_unpack": 0,
     }
 
 
 KERNEL_NAMES = {"jacobi": "k_jacobi", "forces_diffuse_div": "k_forces_diffuse_div", "project": "k_project",
                 "advect_u": "k_advect(u)", "advect_v": "k_advect(v)", "advect_d": "k_advect(density)", "splat": "k_splat",
-                "project_advect_u": "k_advect_tiled<1>(u) with k_project fused in", "step_fused": "k_step_fused", "other": "other", "halo": "k_halo_push + k_halo_unpack"}
+                "project_advect_u": "k_advect_tiled<1>(u) with k_project fused in", "step_fused": "k_step_fused", "other": "other", "halo": "k_halo_push", "halo_unpack": "k_halo_unpack"}
 
 
 def emitters_for_sequence(s, h, w):
@@ -422,7 +422,7 @@ def kernel_rooflines(ctx, key, prof, K, T, steps, cells_per_launch, clk, fits_l2
     total_ms = sum(v[0] for v in prof.values()) or 1.0
     out = []
     for ph, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-        if not n or ph in ("other", "splat", "halo"):
+        if not n or ph in ("other", "splat", "halo", "halo_unpack"):
             continue
         sweeps = K * T * steps / n if ph == "jacobi" else 0
         nsteps = T * steps / n if ph == "step_fused" else 1
@@ -446,7 +446,7 @@ def kernel_rooflines(ctx, key, prof, K, T, steps, cells_per_launch, clk, fits_l2
 
 def contract_roofline(ctx, key, prof, K, T, steps, cells_per_launch, kernels):
     """The `roofline` object of the contract: dominant kernel, algorithmic bytes per launch / mean launch duration / HBM peak."""
-    dom = max((k for k in prof if prof[k][1] > 0 and k not in ("other", "splat", "halo")), key=lambda k: prof[k][0])
+    dom = max((k for k in prof if prof[k][1] > 0 and k not in ("other", "splat", "halo", "halo_unpack")), key=lambda k: prof[k][0])
     dom_ms, dom_n = prof[dom]
     total_ms = sum(v[0] for v in prof.values())
     sweeps = K * T * steps / dom_n if dom == "jacobi" else 0

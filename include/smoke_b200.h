@@ -125,7 +125,7 @@ SMK_API int smk_reload_env(void);
 enum {
     SMK_PH_SPLAT = 0, SMK_PH_FORCES_DIFFUSE_DIV, SMK_PH_JACOBI, SMK_PH_PROJECT,
     SMK_PH_ADVECT_U, SMK_PH_ADVECT_V, SMK_PH_ADVECT_D, SMK_PH_OTHER, SMK_PH_STEP_FUSED, SMK_PH_HALO, SMK_PH_PROJECT_ADVECT_U,
-    SMK_PH_COUNT
+    SMK_PH_HALO_UNPACK, SMK_PH_COUNT
 };
 SMK_API int smk_profile_begin(int32_t max_records);
 SMK_API int smk_profile_end(double* ms_per_phase_host, int64_t* launches_per_phase_host, int32_t nphases);

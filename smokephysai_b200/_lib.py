@@ -203,7 +203,7 @@ def launch_count():
 
 
 PHASES = ("splat", "forces_diffuse_div", "jacobi", "project", "advect_u", "advect_v", "advect_d", "other", "step_fused", "halo",
-          "project_advect_u")
+          "project_advect_u", "halo_unpack")
 
 
 def profile_begin(max_records=4096):

@@ -24,6 +24,7 @@
 // simulation that straddles a piece boundary is handed from one CTA to another through global memory.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 #include "common.cuh"
 #include "jacobi_core.cuh"
@@ -663,7 +664,7 @@ template <int NC> struct ClusterCfg {
     static constexpr int RB = 128 / NC, NW = 16, NT = NW * 32, R = RB / NW;
     static constexpr int SU_ROWS = RB + 2 * CH + 1, SV_ROWS = RB + 2 * CH, SD_ROWS = RB + 2 * CH;
     static constexpr int SU = SU_ROWS * FZ_PU, SV = SV_ROWS * FZ_PV, SD = SD_ROWS * FZ_PD;       // floats
-    static constexpr size_t SMEM = (size_t)(SU + SV + SD) * 4 + sizeof(float4) * (2 * 2 * NW * 32 + 2 * 2 * 32) + 4 * sizeof(unsigned long long);
+    static constexpr size_t SMEM = (size_t)(SU + SV + SD) * 4 + sizeof(float4) * (2 * 2 * NW * 32 + 2 * 2 * 2 * 32) + 4 * sizeof(unsigned long long);
 };
 
 // zdiffuse_strip for a strip of R rows
@@ -829,8 +830,9 @@ k_step_cluster(const FusedArgs a)
     float* sv_s = su_s + C::SU;
     float* sd_s = sv_s + C::SV;
     float4 (*halo)[2][NW][32] = reinterpret_cast<float4 (*)[2][NW][32]>(sd_s + C::SD);
-    float4 (*xp)[2][32] = reinterpret_cast<float4 (*)[2][32]>(reinterpret_cast<float4*>(sd_s + C::SD) + 2 * 2 * NW * 32);   // [parity][0: from above, 1: from below]
-    unsigned long long* mb = reinterpret_cast<unsigned long long*>(reinterpret_cast<float4*>(sd_s + C::SD) + 2 * 2 * NW * 32 + 2 * 2 * 32);   // mb[parity * 2 + side]
+    // rows from the neighbouring CTAs: xp[slot][0: from above, 1: from below][0: the row nearer to this band, 1: the one beyond][lane]
+    float4 (*xp)[2][2][32] = reinterpret_cast<float4 (*)[2][2][32]>(reinterpret_cast<float4*>(sd_s + C::SD) + 2 * 2 * NW * 32);
+    unsigned long long* mb = reinterpret_cast<unsigned long long*>(reinterpret_cast<float4*>(sd_s + C::SD) + 2 * 2 * NW * 32 + 2 * 2 * 2 * 32);   // mb[slot * 2 + side]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = (int)cluster_rank();
@@ -866,20 +868,25 @@ k_step_cluster(const FusedArgs a)
     fv.last = fd.last = c * RB + RB - 1;
     fu.last = last_cta ? 128 : c * RB + RB - 1;
     float* const su = fu.mine; float* const sv = fv.mine; float* const sd = fd.mine;
-    // Jacobi boundary rows between CTAs: this CTA's first row goes to the upper neighbour's xp[parity][1][lane] and signals its
-    // mb[parity][1]; the last row goes to the lower neighbour's xp[parity][0][lane] / mb[parity][0] (st.async: data + signal)
+    // Jacobi rows between CTAs, TWO rows per side every two sweeps (see the sweep loop): this CTA's first two rows go to the upper
+    // neighbour's xp[slot][1][.][lane] and signal its mb[slot][1]; the last two rows go to the lower neighbour's xp[slot][0][.][lane]
+    // / mb[slot][0] (st.async: data + signal).  slot = exchange number & 1.
+#ifdef SMK_CL_NOEXCH                          // probe builds only (tools/micro/cluster_probe.cu): what a sweep costs without the rows from the neighbouring CTAs
+    const bool has_up = false, has_dn = false;
+#else
     const bool has_up = c > 0, has_dn = !last_cta;
-    const unsigned rxp_up = has_up ? cluster_map32(csmem(&xp[0][1][lane]), c - 1) : 0u, rmb_up = has_up ? cluster_map32(csmem(&mb[1]), c - 1) : 0u;
-    const unsigned rxp_dn = has_dn ? cluster_map32(csmem(&xp[0][0][lane]), c + 1) : 0u, rmb_dn = has_dn ? cluster_map32(csmem(&mb[0]), c + 1) : 0u;
-    constexpr unsigned XP_PAR = 2 * 32 * sizeof(float4), MB_PAR = 2 * sizeof(unsigned long long);      // byte distance of the parity-1 copies
+#endif
+    const unsigned rxp_up = has_up ? cluster_map32(csmem(&xp[0][1][0][lane]), c - 1) : 0u, rmb_up = has_up ? cluster_map32(csmem(&mb[1]), c - 1) : 0u;
+    const unsigned rxp_dn = has_dn ? cluster_map32(csmem(&xp[0][0][0][lane]), c + 1) : 0u, rmb_dn = has_dn ? cluster_map32(csmem(&mb[0]), c + 1) : 0u;
+    constexpr unsigned XP_SLOT = 2 * 2 * 32 * sizeof(float4), XP_ROW = 32 * sizeof(float4), MB_SLOT = 2 * sizeof(unsigned long long);
     const unsigned mb_local = csmem(mb);
-    unsigned phase = 0;                       // bit (parity * 2 + side): the phase parity this thread waits for next on mb[parity][side]
+    unsigned nex = 0;                         // exchanges posted so far (the same number in every thread of the cluster)
     if (tid == 0) {
         for (int k = 0; k < 4; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb_local + 8u * k) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // a row is 32 lanes x 16 bytes; every barrier is armed for its first use here and re-armed by its consumer after each use
+        // two rows of 32 lanes x 16 bytes; every barrier is armed for its first use here and re-armed by its consumer after each use
         for (int k = 0; k < 4; ++k)
-            if ((k & 1) ? has_dn : has_up) cmbar_arm(mb_local + 8u * k, 512u);
+            if ((k & 1) ? has_dn : has_up) cmbar_arm(mb_local + 8u * k, 1024u);
     }
     // rows of the stored windows that exist in the grid
     const int slo = max(g0, 0);
@@ -1005,54 +1012,99 @@ k_step_cluster(const FusedArgs a)
                 ua = ub;
             }
         }
+        // ... and of the row just above / below the band (halo rows of u and v), which the first and the last warp sweep redundantly
+        float4 Dx = zero4;
+        if ((warp == 0 && has_up) || (warp == NW - 1 && has_dn)) {
+            const int i = warp == 0 ? c * RB - 1 : c * RB + RB;
+            const float4 ua = zlds4(su + i * FZ_PU + c0), ub = zlds4(su + (i + 1) * FZ_PU + c0);
+            const float4 va = zlds4(sv + i * FZ_PV + c0);
+            const float vr = sv[i * FZ_PV + c0 + 4];
+            float4 o;
+            o.x = ((ub.x - ua.x) + va.y) - va.x;
+            o.y = ((ub.y - ua.y) + va.z) - va.y;
+            o.z = ((ub.z - ua.z) + va.w) - va.z;
+            o.w = ((ub.w - ua.w) + vr) - va.w;
+            Dx = zdiv4(o, fzdiv);
+        }
 
         CL_TICK(2);
-        // ---- a6 K Jacobi sweeps.  A warp's boundary rows are computed first and posted at once: to the neighbouring warps through
-        //      shared memory (published by the CTA barrier at the end of the sweep), to the neighbouring CTA by st.async, which
-        //      signals that CTA's mbarrier by itself.  Only the two warps at the ends of the band ever wait for another CTA, at
-        //      the start of the next sweep, by when the row has had a whole sweep to arrive.  No cluster barrier in the loop.
-        //      Two copies (sweep parity) of every line: a line is rewritten two sweeps after it was read, and its writer cannot
-        //      be two sweeps ahead of its reader (it needs the reader's row of the sweep in between).                :139-145
-        auto post = [&](const int q, const float4 first, const float4 last) {       // lines that sweeps of parity q read
-            halo[q][0][warp][lane] = first;
-            halo[q][1][warp][lane] = last;
-            if (warp == 0 && has_up) st_async_f4(rxp_up + q * XP_PAR, first, rmb_up + q * MB_PAR);
-            if (warp == NW - 1 && has_dn) st_async_f4(rxp_dn + q * XP_PAR, last, rmb_dn + q * MB_PAR);
+        // ---- a6 K Jacobi sweeps                                                                                   :139-145
+        // Within a CTA: a warp computes its boundary rows first and posts them to the neighbouring warps through shared memory, the CTA
+        // barrier at the end of the sweep publishes them (two copies of every line, by sweep parity).
+        // Between CTAs: a sweep of a band needs the neighbouring band's boundary row of the sweep before, and one SM -> SM hop costs
+        // ~700 cycles from st.async to the waiter's wake-up -- with an exchange per sweep a sweep took 845 cycles, 60 % of the step
+        // (tools/micro/cluster_probe.cu; a cluster barrier per sweep was worse still: barrier.cluster.arrive.release compiles to
+        // MEMBAR.ALL.GPU + UCGABAR, ~0.7 us; {value, tag} 8-byte DSMEM stores polled by the reader took 1420 cycles per sweep).
+        // So the hop is paid every SECOND sweep: an exchange carries the two rows next to the band (state s, s even); the first
+        // and the last warp sweep the row just outside the band redundantly in sweep s (they hold its divergence, Dx), which
+        // gives them the state s + 1 of that row for sweep s + 1; after sweep s + 1 the next two rows travel.  Two slots
+        // (exchange number & 1): a slot is rewritten two exchanges after it was read, and its writer cannot be two exchanges
+        // ahead of its reader (it needs the reader's rows of the exchange in between).
+        auto post_cta = [&]() {                             // this band's first / last two rows (current state) to the neighbours
+            const unsigned slot = nex & 1u;
+            if (warp == 0 && has_up) {                      // they are the upper neighbour's rows below its band: nearer row first
+                st_async_f4(rxp_up + slot * XP_SLOT, P[0], rmb_up + slot * MB_SLOT);
+                st_async_f4(rxp_up + slot * XP_SLOT + XP_ROW, P[1], rmb_up + slot * MB_SLOT);
+            }
+            if (warp == NW - 1 && has_dn) {                 // the lower neighbour's rows above its band: nearer row (my last) first
+                st_async_f4(rxp_dn + slot * XP_SLOT, P[R - 1], rmb_dn + slot * MB_SLOT);
+                st_async_f4(rxp_dn + slot * XP_SLOT + XP_ROW, P[R - 2], rmb_dn + slot * MB_SLOT);
+            }
+            ++nex;
         };
-        auto from_above = [&](const int q) -> float4 {                              // row above this warp's strip, parity q
-            if (warp > 0) return halo[q][1][warp - 1][lane];
-            if (!has_up) return zero4;
-            const unsigned bit = 1u << (q * 2);
-            cmbar_wait(mb_local + 8u * (q * 2), (phase & bit) ? 1u : 0u);
-            phase ^= bit;
-            const float4 v = xp[q][0][lane];
+        // the latest exchange from the neighbour on `side` (0 above, 1 below): wait for it, read both rows, re-arm the barrier
+        auto from_cta = [&](const int side, float4& near_row, float4& far_row) {
+            const unsigned x = nex - 1u, slot = x & 1u;     // slot k is used by exchanges k, k + 2, ...: the m-th use has phase parity m & 1
+            cmbar_wait(mb_local + 8u * (slot * 2 + side), (x >> 1) & 1u);
+            near_row = xp[slot][side][0][lane];
+            far_row = xp[slot][side][1][lane];
             __syncwarp();
-            if (lane == 0) cmbar_arm(mb_local + 8u * (q * 2), 512u);
-            return v;
+            if (lane == 0) cmbar_arm(mb_local + 8u * (slot * 2 + side), 1024u);
         };
-        auto from_below = [&](const int q) -> float4 {
-            if (warp < NW - 1) return halo[q][0][warp + 1][lane];
-            if (!has_dn) return zero4;
-            const unsigned bit = 1u << (q * 2 + 1);
-            cmbar_wait(mb_local + 8u * (q * 2 + 1), (phase & bit) ? 1u : 0u);
-            phase ^= bit;
-            const float4 v = xp[q][1][lane];
-            __syncwarp();
-            if (lane == 0) cmbar_arm(mb_local + 8u * (q * 2 + 1), 512u);
-            return v;
-        };
-        post(0, P[0], P[R - 1]);
+        static_assert(R >= 2, "an exchange carries two rows of one warp");
+        halo[0][0][warp][lane] = P[0];
+        halo[0][1][warp][lane] = P[R - 1];
+        post_cta();
         __syncthreads();
-        for (int s = 0; s < a.K; ++s) {
-            const int q = s & 1;
-            const float4 up = from_above(q), dn = from_below(q);
-            // boundary rows first (for R <= 2 every row is one), posted at once; then the rows in between.  Row r is on the ring (and
-            // stays zero) when its global index is 0 or 127: the mask multiplies by 0 instead of 0.25, like every other Jacobi kernel here.
-            const bool ok0 = r0 >= 1 && r0 <= h - 2, okL = r0 + R - 1 >= 1 && r0 + R - 1 <= h - 2;
+        float4 X1 = zero4;                                  // first warp: state of the row above the band; last warp: of the row below it
+        // A sweep is issue-bound here (4 warps per scheduler, ~40 flops per thread), so everything that does not change from sweep to
+        // sweep is hoisted: ring masks of the two boundary rows, the addresses of the lines, and the parity (two sweeps per trip).
+        const bool ok0 = r0 >= 1 && r0 <= h - 2, okL = r0 + R - 1 >= 1 && r0 + R - 1 <= h - 2;
+        const float m0[4] = {ok0 ? cm[0] : 0.f, ok0 ? cm[1] : 0.f, ok0 ? cm[2] : 0.f, ok0 ? cm[3] : 0.f};
+        const float mL[4] = {okL ? cm[0] : 0.f, okL ? cm[1] : 0.f, okL ? cm[2] : 0.f, okL ? cm[3] : 0.f};
+        const float4* const rd_up = &halo[0][1][warp > 0 ? warp - 1 : 0][lane];         // + HPAR for the lines of parity 1
+        const float4* const rd_dn = &halo[0][0][warp < NW - 1 ? warp + 1 : 0][lane];
+        float4* const wr_first = &halo[0][0][warp][lane];
+        float4* const wr_last = &halo[0][1][warp][lane];
+        constexpr int HPAR = 2 * NW * 32;                   // float4 between the two parities of a line
+        const bool edge_up = warp == 0 && has_up, edge_dn = warp == NW - 1 && has_dn;
+        auto sweep = [&](auto parity) {
+            constexpr int q = decltype(parity)::value;
+            float4 up = warp > 0 ? rd_up[q * HPAR] : zero4;
+            float4 dn = warp < NW - 1 ? rd_dn[q * HPAR] : zero4;
+            if (q == 0) {
+                // even sweep: the neighbour's two rows arrive; sweep the nearer one here too (it is an interior row of the grid)
+                if (edge_up) {
+                    float4 x2;
+                    from_cta(0, up, x2);
+                    X1 = stencil_row(x2, up, P[0], Dx, cm[0], cm[1], cm[2], cm[3]);
+                }
+                if (edge_dn) {
+                    float4 x2;
+                    from_cta(1, dn, x2);
+                    X1 = stencil_row(P[R - 1], dn, x2, Dx, cm[0], cm[1], cm[2], cm[3]);
+                }
+            } else {
+                if (edge_up) up = X1;
+                if (edge_dn) dn = X1;
+            }
+            // boundary rows first (for R = 2 every row is one), posted at once; then the rows in between.  A row on the ring (global
+            // row 0 or 127) stays zero: its mask multiplies by 0 instead of 0.25, like in every other Jacobi kernel here.
             const float4 o0 = P[0], oL = P[R - 1];
-            const float4 n0 = stencil_row(up, o0, R > 1 ? P[1] : dn, Dv[0], ok0 ? cm[0] : 0.f, ok0 ? cm[1] : 0.f, ok0 ? cm[2] : 0.f, ok0 ? cm[3] : 0.f);
-            const float4 nL = R > 1 ? stencil_row(P[R - 2], oL, dn, Dv[R - 1], okL ? cm[0] : 0.f, okL ? cm[1] : 0.f, okL ? cm[2] : 0.f, okL ? cm[3] : 0.f) : n0;
-            post(q ^ 1, n0, nL);
+            const float4 n0 = stencil_row(up, o0, P[1], Dv[0], m0[0], m0[1], m0[2], m0[3]);
+            const float4 nL = stencil_row(P[R - 2], oL, dn, Dv[R - 1], mL[0], mL[1], mL[2], mL[3]);
+            wr_first[(q ^ 1) * HPAR] = n0;
+            wr_last[(q ^ 1) * HPAR] = nL;
             float4 prev = o0;
 #pragma unroll
             for (int r = 1; r < R - 1; ++r) {                                      // interior rows are never ring rows (R divides the band)
@@ -1062,18 +1114,34 @@ k_step_cluster(const FusedArgs a)
                 prev = cur;
             }
             P[0] = n0;
-            if (R > 1) P[R - 1] = nL;
+            P[R - 1] = nL;
+            if (q == 1) post_cta();                         // the state after an even number of sweeps travels
+#ifndef SMK_CL_NOBAR                          // probe builds only
             __syncthreads();
+#endif
+        };
+        {
+            int s = 0;
+            for (; s + 1 < a.K; s += 2) {
+                sweep(std::integral_constant<int, 0>());
+                sweep(std::integral_constant<int, 1>());
+            }
+            if (s < a.K) sweep(std::integral_constant<int, 0>());
         }
 
         CL_TICK(3);
         // ---- a7 gradient subtract on the owned rows, then the neighbours' halo rows of u and v                   :148-149
         {
-            // the lines posted by the last sweep (parity K & 1): the row above comes from them; the row below is not needed here, but
-            // the line from the CTA below has to be consumed so that its mbarrier stays in step with the sweeps of the next step
+            // the row above this warp's strip after K sweeps: from the warp above (lines of parity K & 1); for the first warp of a band
+            // from the CTA above -- after an odd K it is the row swept redundantly here (X1), after an even K it comes with the exchange
+            // posted after the last sweep, which the last warp has to consume as well to keep its barrier in step
             const int q = a.K & 1;
-            float4 pabove = from_above(q);
-            if (warp == NW - 1 && has_dn) (void)from_below(q);
+            float4 pabove = warp > 0 ? halo[q][1][warp - 1][lane] : zero4;
+            if (warp == 0 && has_up) {
+                if (a.K & 1) pabove = X1;
+                else { float4 x2; from_cta(0, pabove, x2); }
+            }
+            if (warp == NW - 1 && has_dn && !(a.K & 1)) { float4 x1, x2; from_cta(1, x1, x2); }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int i = r0 + r;

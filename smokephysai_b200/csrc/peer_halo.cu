@@ -149,7 +149,7 @@ static int peer_xfer(const smk_peer_comm_t* c, float* const* base, bool push, cu
     for (int k = 0; k < a.n; ++k) most = most > a.c[k].n4 ? most : a.c[k].n4;
     int per = (int)((most + 256 * 4 - 1) / (256 * 4));       // four 16-byte elements per thread
     per = per < 1 ? 1 : (per > 32 ? 32 : per);               // at most 8 x 32 = 256 CTAs of 256 threads: all co-resident (2 per SM)
-    ProfScope prof_(SMK_PH_HALO, s);
+    ProfScope prof_(push ? SMK_PH_HALO : SMK_PH_HALO_UNPACK, s);      // the unpack's time includes the wait for the slower neighbour
     if (push) launch_chain(k_halo_xfer<true>, dim3(per, a.n), dim3(256), 0, s, a);
     else      launch_chain(k_halo_xfer<false>, dim3(per, a.n), dim3(256), 0, s, a);
     return check_launch(push ? "k_halo_push" : "k_halo_unpack");
