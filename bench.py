@@ -444,7 +444,7 @@ def kernel_rooflines(ctx, key, prof, K, T, steps, cells_per_launch, clk, fits_l2
     return out, fp32_peak
 
 
-def contract_roofline(ctx, key, prof, K, T, steps, cells_per_launch, kernels):
+def contract_roofline(ctx, key, prof, K, T, steps, cells_per_launch, kernels, rename=None):
     """The `roofline` object of the contract: dominant kernel, algorithmic bytes per launch / mean launch duration / HBM peak."""
     dom = max((k for k in prof if prof[k][1] > 0 and k not in ("other", "splat", "halo", "halo_unpack")), key=lambda k: prof[k][0])
     dom_ms, dom_n = prof[dom]
@@ -453,7 +453,8 @@ def contract_roofline(ctx, key, prof, K, T, steps, cells_per_launch, kernels):
     nsteps = T * steps / dom_n if dom == "step_fused" else 1
     alg = phase_bytes_per_cell(K, sweeps, nsteps)[dom] * cells_per_launch
     achieved = alg / (dom_ms / dom_n * 1e-3) / 1e9
-    k = next(e for e in kernels if e["kernel"] == KERNEL_NAMES[dom])
+    kname = rename if (rename and dom == "step_fused") else KERNEL_NAMES[dom]
+    k = next(e for e in kernels if e["kernel"] == kname)
     if dom == "jacobi":
         note = ("achieved > peak is possible: %d sweeps are fused per launch with the pressure tile on-chip, so real DRAM "
                 "traffic is below the algorithmic 12 B/cell-sweep (see `traffic`); `binding` names what limits the kernel" % round(sweeps))
@@ -464,7 +465,7 @@ def contract_roofline(ctx, key, prof, K, T, steps, cells_per_launch, kernels):
                 % (round(nsteps), 100 + 12 * K))
     else:
         note = ""
-    r = {"bound": "hbm", "kernel": KERNEL_NAMES[dom], "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
+    r = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
          "traffic": k["traffic"], "peak_source": ctx.peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": dom_ms / dom_n,
          "launches_timed": int(dom_n), "share_of_step": dom_ms / total_ms,
          "binding": {"bound": k["bound"], "frac": k["frac"],
@@ -546,7 +547,13 @@ def run_batched(ctx, key, steps, warmup):
 
     fused = ns.step_is_fused(T)
     cells_per_launch = B * h * w
-    kernels, fp32_peak = kernel_rooflines(ctx, key if key != "c2s" else "c2", prof, K, T, steps, cells_per_launch, clk, fits_l2)
+    clustered = key == "c2s" and fused and B * 4 <= ctx.sm_count - 16          # k_step_cluster runs these: its own traffic capture
+    kernels, fp32_peak = kernel_rooflines(ctx, "c2_strong" if clustered else ("c2" if key == "c2s" else key), prof, K, T, steps,
+                                          cells_per_launch, clk, fits_l2)
+    if clustered:
+        for e in kernels:
+            if e["kernel"] == "k_step_fused":
+                e["kernel"] = "k_step_cluster<4>"
     step_bytes, step_flops = 100 + 12 * K, 118 + 5 * K
     per_gpu = value / ctx.world
     out = {
@@ -564,7 +571,7 @@ def run_batched(ctx, key, steps, warmup):
                        "api": "SmokeSimulator.generate_sequences(host emitter lists, to_host=False) -> frames stay in HBM, consumed "
                               "by a device-side reduction (the simulator -> model hand-off of train.py:59-80)"},
         "gpu_launches": int(launches),
-        "roofline": contract_roofline(ctx, key, prof, K, T, steps, cells_per_launch, kernels),
+        "roofline": contract_roofline(ctx, key, prof, K, T, steps, cells_per_launch, kernels, "k_step_cluster<4>" if clustered else None),
         "kernels": kernels,
         "roofline_step": {"algorithmic_bytes_per_cell_step": step_bytes, "achieved": per_gpu * step_bytes / 1e9, "peak": ctx.peak,
                           "unit": "GB/s", "frac": per_gpu * step_bytes / 1e9 / ctx.peak, "per": "GPU"},

@@ -130,58 +130,37 @@ __device__ __forceinline__ float4 zmask4(float4 v, const int c0, const int cols)
     return v;
 }
 
-// Four IEEE quotients n / d (navier_stokes.py:136 divides by dt).  nvcc's div.rn.f32 is, per quotient: MUFU.RCP of the divisor, two
-// FFMA that refine it to r1, then q0 = n * r1, rem = fma(q0, -d, n), q = fma(r1, rem, q0) -- guarded by FCHK and a branch to a
-// ~100-instruction subroutine for operands or quotients near the denormal range: 13 instructions and a reconvergence point per
-// quotient, 416 of the 612 instructions of the divergence phase.  The divisor is dt in every one of them, so FzDiv computes r1
-// ONCE per kernel with the very same three instructions and a quotient costs the three-instruction tail: bit-identical to
-// div.rn.f32's own fast path (it is that path).  Its validity range is enforced here instead of by FCHK:
-//   * |d| in [1e-6, 1e6] and d's significand not all ones (the one divisor class for which the tail can miss the rounding:
-//     Markstein's exception; checked on the CPU over all 2^31 numerators for r1 one ulp either side) -- else `fast` is false
-//     and every quotient takes the fp64 route below;
-//   * |n| in [1e-25, 1e25] or n == 0: quotient, remainder and products stay normal or exactly representable.  A warp that holds
-//     any other numerator (the thin ring where the diffusing velocities underflow) takes (float)((double)n / (double)d), the
-//     correctly rounded fp32 quotient for every finite n, d (53 >= 2*24 + 2 bits make the double rounding innocuous, denormal
-//     results included: a quotient of two 24-bit significands is either a rounding midpoint or at least 2^-48 away from one).
-struct FzDiv { float d, r1; bool fast; };
-__device__ __forceinline__ FzDiv zdiv_setup(const float d)
-{
-    FzDiv k;
-    k.d = d;
-    float r0;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d));
-    const float e = __fmaf_rn(r0, -d, 1.0f);
-    k.r1 = __fmaf_rn(r0, e, r0);
-    const float ad = fabsf(d);
-    k.fast = ad >= 1e-6f && ad <= 1e6f && (__float_as_uint(d) & 0x7fffffu) < 0x7ffffeu;
-    return k;
-}
+// Four IEEE quotients n / d (navier_stokes.py:136 divides by dt).  nvcc's div.rn.f32 has a fast path (three FFMAs
+// around a reciprocal) and, for operands or quotients near the denormal range, a ~100-instruction subroutine; the
+// thin ring where the diffusing velocities underflow sends whole warps there every step.  Those warps take an
+// fp64 division instead: (float)((double)n / (double)d) is the correctly rounded fp32 quotient for every finite
+// n, d (53 >= 2*24 + 2 bits makes the double rounding innocuous, denormal results included: a quotient of two
+// 24-bit significands is either exactly a rounding midpoint or at least 2^-48 away from it in relative terms).
 __device__ __forceinline__ bool zdiv_odd(const float x)
 {
     const float ax = fabsf(x);
-    return ax != 0.0f && !(ax >= 1e-25f && ax <= 1e25f);
+    return ax != 0.0f && !(ax >= 1e-30f && ax <= 1e30f);
 }
-__device__ __forceinline__ float zdiv1(const float n, const FzDiv& k)
-{
-    const float q0 = __fmaf_rn(n, k.r1, 0.0f);
-    const float rem = __fmaf_rn(q0, -k.d, n);
-    return __fmaf_rn(k.r1, rem, q0);
-}
-__device__ __forceinline__ float4 zdiv4(float4 n, const FzDiv& k)
+__device__ __forceinline__ float4 zdiv4(float4 n, const float d)
 {
 #ifdef SMK_PROBE_NODIV               // tools/micro only: what the step costs without the division (wrong results)
-    n.x *= k.d; n.y *= k.d; n.z *= k.d; n.w *= k.d;
+    n.x *= d; n.y *= d; n.z *= d; n.w *= d;
     return n;
 #endif
-    if (!k.fast || __any_sync(0xffffffffu, zdiv_odd(n.x) || zdiv_odd(n.y) || zdiv_odd(n.z) || zdiv_odd(n.w))) {
-        const double dd = (double)k.d;
+    if (__any_sync(0xffffffffu, zdiv_odd(n.x) || zdiv_odd(n.y) || zdiv_odd(n.z) || zdiv_odd(n.w))) {
+        const double dd = (double)d;
         n.x = (float)((double)n.x / dd); n.y = (float)((double)n.y / dd);
         n.z = (float)((double)n.z / dd); n.w = (float)((double)n.w / dd);
     } else {
-        n.x = zdiv1(n.x, k); n.y = zdiv1(n.y, k); n.z = zdiv1(n.z, k); n.w = zdiv1(n.w, k);
+        n.x = n.x / d; n.y = n.y / d; n.z = n.z / d; n.w = n.w / d;
     }
     return n;
 }
+// (Round 2 tried to hoist the reciprocal refinement of div.rn.f32 out of the quotients -- MUFU.RCP + two FFMA once per kernel, then
+//  the three-FFMA tail per quotient, bit-identical to the compiler's own fast path and verified on the CPU over all 2^31 numerators
+//  of dt = 0.01 -- with the validity range enforced by an explicit per-warp test instead of FCHK.  The divergence phase shrank from
+//  612 to ~470 executed instructions, but c2 ran 1.8 % SLOWER (50.6 against 51.5 G cell-steps/s): the range test needs three
+//  compares per value where FCHK needs one instruction, and the compiler had merged the two branches below into one stream.)
 
 // advection_step at one cell (navier_stokes.py:74-131): same restatement as k_advect (stencil.cu) with the
 // field, u and v in shared memory.  rows x cols is the advected field, h x w the cell grid.
@@ -306,7 +285,6 @@ k_step_fused(const FusedArgs a)
     const bool xu = (h == 128) && lane < 8 && xe < w;
     const bool xv = (w == 128) && lane < 8 && xe < h;
     const float dt = a.dt;
-    const FzDiv fzdiv = zdiv_setup(dt);
 #ifdef SMK_FUSED_TIMING
     long long tick0_ = clock64();
 #endif
@@ -448,7 +426,7 @@ k_step_fused(const FusedArgs a)
                 o.y = ((ub.y - ua.y) + va.z) - va.y;
                 o.z = ((ub.z - ua.z) + va.w) - va.z;
                 o.w = ((ub.w - ua.w) + vr) - va.w;
-                o = zdiv4(o, fzdiv);
+                o = zdiv4(o, dt);
                 if (!FULL) {
                     if (i >= h) o = zero4;
                     if (c0 + 0 >= w) o.x = 0.f;
@@ -845,7 +823,6 @@ k_step_cluster(const FusedArgs a)
     float* __restrict__ gD = a.D + b * a.sc_;
     float* __restrict__ gP = a.P + b * a.sc_;
     const float dt = a.dt;
-    const FzDiv fzdiv = zdiv_setup(dt);
 #ifdef SMK_FUSED_TIMING
     long long tick0_ = clock64();
 #define CL_TICK(k) do { if (tid == 0 && blockIdx.x == 0) { const long long t1_ = clock64(); a.ticks[k] += t1_ - tick0_; tick0_ = t1_; } } while (0)
@@ -1008,7 +985,7 @@ k_step_cluster(const FusedArgs a)
                 o.y = ((ub.y - ua.y) + va.z) - va.y;
                 o.z = ((ub.z - ua.z) + va.w) - va.z;
                 o.w = ((ub.w - ua.w) + vr) - va.w;
-                Dv[r] = zdiv4(o, fzdiv);
+                Dv[r] = zdiv4(o, dt);
                 ua = ub;
             }
         }
@@ -1024,7 +1001,7 @@ k_step_cluster(const FusedArgs a)
             o.y = ((ub.y - ua.y) + va.z) - va.y;
             o.z = ((ub.z - ua.z) + va.w) - va.z;
             o.w = ((ub.w - ua.w) + vr) - va.w;
-            Dx = zdiv4(o, fzdiv);
+            Dx = zdiv4(o, dt);
         }
 
         CL_TICK(2);
