@@ -192,7 +192,13 @@ k_jacobi_packed(const float* __restrict__ pin, float* __restrict__ pout, const f
 //            shuffles and halo LDS/STS.
 // shared memory of a CTA of NW warps (tile = 8 NW x 128): staged pressure, staged divergence, halo lines, mbarrier, arguments
 __host__ __device__ constexpr size_t js_bar_off(const int NW) { return (size_t)2 * 8 * NW * 128 * 4 + sizeof(float4) * 2 * 2 * NW * 32; }
-__host__ __device__ constexpr size_t js_smem_bytes(const int NW) { return js_bar_off(NW) + 16 + 96; }
+__host__ __device__ constexpr size_t js_out_off(const int NW) { return js_bar_off(NW) + 128; }      // mbarrier (16 B), arguments (<= 112 B)
+// TMA kernels also stage the rows and columns of a tile that survive the launch -- (8 NW - 2 T) x (128 - 2 HX), dense -- for one
+// cp.async.bulk.tensor store per tile
+__host__ __device__ constexpr size_t js_smem_bytes(const int NW, const int T = 0, const int HX = 0, const bool tma = false)
+{
+    return js_out_off(NW) + (tma ? (size_t)(8 * NW - 2 * T) * (128 - 2 * HX) * 4 : 0);
+}
 
 __device__ __forceinline__ void js_cp_async16_zfill(float* smem_dst, const float* gmem_src, const unsigned src_bytes)
 {
@@ -270,7 +276,7 @@ __device__ __forceinline__ void js_stage(const JsArgs& a, const CUtensorMap* mp,
 // float2 elements, ptxas kept the f32x2 operands in unpaired registers and predicated the ring rows with selects
 // (52 MOV + 36 FSEL per sweep and warp, +37 % instructions: profiles/r01j_*).
 template <int PMASK, bool TMA, bool RING, class E, int NW>
-__device__ __noinline__ void js_tile(const JsArgs& a, const CUtensorMap* mp, const CUtensorMap* md, float* js_smem,
+__device__ __noinline__ void js_tile(const JsArgs& a, const CUtensorMap* mp, const CUtensorMap* md, const CUtensorMap* mo, float* js_smem,
                                      const JsTile c, const JsTile cnext, const bool has_next, const unsigned parity)
 {
     constexpr int R = 8, TH = R * NW;
@@ -311,6 +317,8 @@ __device__ __noinline__ void js_tile(const JsArgs& a, const CUtensorMap* mp, con
     // LDGSTS: a thread only overwrites its own strip, no barrier needed; the TMA loads overwrite the whole buffer, so they
     // are issued after the barrier that every thread passes once its strip is read.
     if (!TMA && has_next) js_stage<false, NW>(a, mp, md, js_smem, cnext);
+    // the bulk store of the previous tile has read the output staging buffer before anybody passes the barrier below
+    if (TMA && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();
     if (TMA && has_next) js_stage<true, NW>(a, mp, md, js_smem, cnext);
     int s = 0;
@@ -336,25 +344,51 @@ __device__ __noinline__ void js_tile(const JsArgs& a, const CUtensorMap* mp, con
         A = B;
     }
 
-    const int vx0 = x0 + (c.bx > 0 ? a.HX : 0);
-    const int vx1 = (c.bx + 1 < a.nx) ? x0 + 128 - a.HX : a.pitch;
-    const int vy0 = y0 + (c.by > 0 ? T : 0);
-    const int vy1 = (c.by + 1 < a.ny) ? y0 + NW * R - T : a.h;
-    if (gj >= vx0 && gj < vx1 && gj < a.pitch) {
-        float* out = a.pout + (size_t)c.bz * (size_t)a.bstride;
+    // A tile with neighbours on all four sides keeps the box [T, TH - T) x [HX, 128 - HX): the TMA kernels write it to a dense
+    // staging buffer (one STS.128 per surviving strip row) and ONE thread hands it to the TMA unit after the barrier that ends
+    // the tile -- no address arithmetic, predicates or 16-byte global stores in the 512 threads.  Tiles on the rim of the
+    // tiling keep more (up to the edge of the grid) and store their strips directly.
+    const bool boxed = TMA && c.bx > 0 && c.bx + 1 < a.nx && c.by > 0 && c.by + 1 < a.ny;
+    if (boxed) {
+        const int bw = 128 - 2 * a.HX;                                                  // box width (floats), a multiple of 4
+        float* so = reinterpret_cast<float*>(reinterpret_cast<char*>(js_smem) + js_out_off(NW));
+        const int cx = 4 * lane - a.HX;
+        if (cx >= 0 && cx < bw) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int gi = gi0 + r;
-            if (gi >= vy0 && gi < vy1 && gi < a.h)
-                *reinterpret_cast<float4*>(out + (size_t)gi * a.pitch + gj) = packed_row(A, r);
+            for (int r = 0; r < R; ++r) {
+                const int ry = warp * R + r - T;
+                if (ry >= 0 && ry < TH - 2 * T) *reinterpret_cast<float4*>(so + ry * bw + cx) = packed_row(A, r);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");               // generic-proxy writes -> visible to the TMA unit
+    } else {
+        const int vx0 = x0 + (c.bx > 0 ? a.HX : 0);
+        const int vx1 = (c.bx + 1 < a.nx) ? x0 + 128 - a.HX : a.pitch;
+        const int vy0 = y0 + (c.by > 0 ? T : 0);
+        const int vy1 = (c.by + 1 < a.ny) ? y0 + NW * R - T : a.h;
+        if (gj >= vx0 && gj < vx1 && gj < a.pitch) {
+            float* out = a.pout + (size_t)c.bz * (size_t)a.bstride;
+    #pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int gi = gi0 + r;
+                if (gi >= vy0 && gi < vy1 && gi < a.h)
+                    *reinterpret_cast<float4*>(out + (size_t)gi * a.pitch + gj) = packed_row(A, r);
+            }
         }
     }
-    __syncthreads();                       // the halo lines are reused by the next tile
+    __syncthreads();                       // the halo lines are reused by the next tile; the staged box is complete
+    if (boxed && threadIdx.x == 0) {
+        const float* so = reinterpret_cast<const float*>(reinterpret_cast<char*>(js_smem) + js_out_off(NW));
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                     :: "l"(mo), "r"(x0 + a.HX), "r"(y0 + T), "r"(c.bz), "r"((unsigned)__cvta_generic_to_shared(so)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
 }
 
 template <int PMASK, bool TMA, int NW>
 __global__ void __launch_bounds__(NW * 32, (NW * 32 <= 256) ? 2 : 1)
-k_jacobi_stream(const __grid_constant__ JsArgs ga, const __grid_constant__ CUtensorMap mp, const __grid_constant__ CUtensorMap md)
+k_jacobi_stream(const __grid_constant__ JsArgs ga, const __grid_constant__ CUtensorMap mp, const __grid_constant__ CUtensorMap md,
+                const __grid_constant__ CUtensorMap mo)
 {
     pdl_prologue();
     extern __shared__ __align__(128) float js_smem[];
@@ -376,16 +410,26 @@ k_jacobi_stream(const __grid_constant__ JsArgs ga, const __grid_constant__ CUten
     if (t >= ga.ntot) return;
     JsTile c = js_coords(ga, t);
     js_stage<TMA, NW>(ga, &mp, &md, js_smem, c);
+    // the next tile of this CTA is gridDim.x further along the (bx fastest, by, bz) order: stepped, not divided out per tile
+    // (the three divisions by run-time values were 3.8 % of the kernel's instructions: profiles/r02j_*)
+    const int step_y = (int)gridDim.x / ga.nx, step_x = (int)gridDim.x - step_y * ga.nx;
     for (; t < ga.ntot; t += gridDim.x, parity ^= 1u) {
         const bool has_next = t + (int)gridDim.x < ga.ntot;
-        const JsTile cnext = has_next ? js_coords(ga, t + gridDim.x) : c;
+        JsTile cnext = c;
+        if (has_next) {
+            cnext.bx += step_x; cnext.by += step_y;
+            if (cnext.bx >= ga.nx) { cnext.bx -= ga.nx; ++cnext.by; }
+            while (cnext.by >= ga.ny) { cnext.by -= ga.ny; ++cnext.bz; }
+        }
         // tiles in the first / last tile row of a simulation hold rows of the Dirichlet ring (or rows outside the grid);
         // every other tile runs the sweeps without the ring-row tests
         const bool ring = c.by == 0 || c.by * ga.oy + 8 * NW > ga.h - 1;
-        if (ring) js_tile<PMASK, TMA, true, JsElem, NW>(a, &mp, &md, js_smem, c, cnext, has_next, parity);
-        else      js_tile<PMASK, TMA, false, JsElem, NW>(a, &mp, &md, js_smem, c, cnext, has_next, parity);
+        if (ring) js_tile<PMASK, TMA, true, JsElem, NW>(a, &mp, &md, &mo, js_smem, c, cnext, has_next, parity);
+        else      js_tile<PMASK, TMA, false, JsElem, NW>(a, &mp, &md, &mo, js_smem, c, cnext, has_next, parity);
         c = cnext;
     }
+    // the staging buffer must outlive the last bulk store's reads, and its writes complete before the grid counts as finished
+    if (TMA && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 static int ntiles(int n, int tile, int halo)
@@ -463,15 +507,16 @@ static js_encode_fn js_encoder()
     }
     return fn;
 }
-// a (pitch, h, batch) fp32 tensor read in 128 x box_rows x 1 boxes; elements outside it are zero-filled
-static int js_make_map(CUtensorMap* m, const smk_grid_t* g, const float* base, const int box_rows)
+// a (pitch, h, batch) fp32 tensor accessed in box_cols x box_rows x 1 boxes; elements outside it are zero-filled on a load and
+// dropped on a store
+static int js_make_map(CUtensorMap* m, const smk_grid_t* g, const float* base, const int box_rows, const int box_cols = 128)
 {
     js_encode_fn enc = js_encoder();
     if (!enc) return SMK_ENOTMA;
     const cuuint64_t dims[3] = {(cuuint64_t)g->pitch_c, (cuuint64_t)g->h, (cuuint64_t)g->batch};
     // the stride of the batch dimension is not used when there is one simulation, but it has to be a valid one
     const cuuint64_t strides[2] = {(cuuint64_t)g->pitch_c * 4u, (g->batch > 1 ? (cuuint64_t)g->stride_c : (cuuint64_t)g->pitch_c * (cuuint64_t)g->h) * 4u};
-    const cuuint32_t box[3] = {128, (cuuint32_t)box_rows, 1}, estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1}, estr[3] = {1, 1, 1};
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -481,15 +526,16 @@ static int js_make_map(CUtensorMap* m, const smk_grid_t* g, const float* base, c
 template <int NW>
 static int launch_stream(const smk_grid_t* g, const float* src, float* dst, const float* div, int t, int HX, int nx, int ny, int mode, cudaStream_t s)
 {
-    constexpr size_t SMEM = js_smem_bytes(NW);
+    constexpr size_t SMEM_MAX = js_smem_bytes(NW, 1, 4, true);                      // the shallowest launch keeps the largest box
+    const size_t SMEM = js_smem_bytes(NW, t, HX, mode != 1);
     constexpr int PER_SM = (NW * 32 <= 256) ? 2 : 1;
     static bool attr_set[64] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 63;
     if (!attr_set[dev] || dev == 63) {
-        cudaError_t e = cudaFuncSetAttribute(k_jacobi_stream<6, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_jacobi_stream<6, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-        if (e != cudaSuccess) return fail((int)e, "k_jacobi_stream: cannot opt in to %zu B of shared memory: %s", SMEM, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(k_jacobi_stream<6, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)js_smem_bytes(NW));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_jacobi_stream<6, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+        if (e != cudaSuccess) return fail((int)e, "k_jacobi_stream: cannot opt in to %zu B of shared memory: %s", SMEM_MAX, cudaGetErrorString(e));
         attr_set[dev] = true;
     }
     const long ntot = (long)nx * ny * g->batch;
@@ -498,16 +544,17 @@ static int launch_stream(const smk_grid_t* g, const float* src, float* dst, cons
     JsArgs a;
     a.pin = src; a.pout = dst; a.div = div; a.h = g->h; a.w = g->w; a.pitch = g->pitch_c; a.bstride = (long long)g->stride_c;
     a.T = t; a.HX = HX; a.ox = 128 - 2 * HX; a.oy = 8 * NW - 2 * t; a.nx = nx; a.ny = ny; a.ntot = (int)ntot;
-    CUtensorMap mp, md;
-    memset(&mp, 0, sizeof mp); memset(&md, 0, sizeof md);
+    CUtensorMap mp, md, mo;
+    memset(&mp, 0, sizeof mp); memset(&md, 0, sizeof md); memset(&mo, 0, sizeof mo);
     if (mode != 1) {
         int rc = js_make_map(&mp, g, src, 8 * NW);
         if (rc == SMK_OK) rc = js_make_map(&md, g, div, 8 * NW);
+        if (rc == SMK_OK) rc = js_make_map(&mo, g, dst, 8 * NW - 2 * t, 128 - 2 * HX);
         if (rc != SMK_OK) return rc;
     }
     ProfScope prof_(SMK_PH_JACOBI, s);
-    if (mode == 1) launch_chain(k_jacobi_stream<6, false, NW>, dim3(ctas), dim3(NW * 32), SMEM, s, a, mp, md);
-    else           launch_chain(k_jacobi_stream<6, true, NW>, dim3(ctas), dim3(NW * 32), SMEM, s, a, mp, md);
+    if (mode == 1) launch_chain(k_jacobi_stream<6, false, NW>, dim3(ctas), dim3(NW * 32), SMEM, s, a, mp, md, mo);
+    else           launch_chain(k_jacobi_stream<6, true, NW>, dim3(ctas), dim3(NW * 32), SMEM, s, a, mp, md, mo);
     return check_launch("k_jacobi_stream");
 }
 

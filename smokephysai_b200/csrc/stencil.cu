@@ -680,12 +680,15 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
             const int x0a = (int)fx0.x, x0b = (int)fx0.y;
             int y0a = (int)fy0.x, y0b = (int)fy0.y;
             float2 f00, f01, f10, f11;
-            if (INTERIOR && !SLAB) {
-                // The window of an interior tile lies inside the field, so a pair whose lower corners are inside the window
-                // (with room for the +1 corners) has x0 + 1 <= cols - 1 and y0 + 1 <= rows - 1: the clamps of the upper corners
-                // (:121, :123) do not bind and the corner offsets are the constants 1 and AT_FP.  Only the pairs that leave
-                // the window clamp, compare and gather from global memory.
-                const int lya = y0a - wy_org, lxa = x0a - wx_org, lyb = y0b - wy_org, lxb = x0b - wx_org;
+            bool gathered = false;
+            if (INTERIOR) {
+                // The window of an interior tile lies inside the field (on a slab: inside the stored rows, and -- k_advect_tiled --
+                // inside the rows that are still exact, so no reach guard can fire here), so a pair whose lower corners are inside
+                // the window (with room for the +1 corners) has x0 + 1 <= cols - 1 and y0 + 1 <= rows - 1: the clamps of the upper
+                // corners (:121, :123) do not bind and the corner offsets are the constants 1 and AT_FP.  Only the pairs that leave
+                // the window clamp, compare and gather from global memory (below).
+                const int yorg = SLAB ? wy_org + a.row0 : wy_org;                    // y0 is a GLOBAL row on a slab
+                const int lya = y0a - yorg, lxa = x0a - wx_org, lyb = y0b - yorg, lxb = x0b - wx_org;
                 const bool inwin = ((unsigned)lya < (unsigned)(AT_FR - 1)) & ((unsigned)lxa < (unsigned)(AT_FP - 1)) &
                                    ((unsigned)lyb < (unsigned)(AT_FR - 1)) & ((unsigned)lxb < (unsigned)(AT_FP - 1));
                 if (inwin) {
@@ -693,25 +696,10 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
                     const float* qb = sF0 + (lyb * AT_FP + lxb);
                     f00 = make_float2(qa[0], qb[0]); f01 = make_float2(qa[1], qb[1]);
                     f10 = make_float2(qa[AT_FP], qb[AT_FP]); f11 = make_float2(qa[AT_FP + 1], qb[AT_FP + 1]);
-                } else {
-                    fx1.x = fminf(fx1.x, xmax); fx1.y = fminf(fx1.y, xmax);
-                    fy1.x = fminf(fy1.x, ymax); fy1.y = fminf(fy1.y, ymax);
-                    const int dxa = (fx1.x != fx0.x) ? 1 : 0, dxb = (fx1.y != fx0.y) ? 1 : 0;
-                    const int dya = (fy1.x != fy0.x) ? 1 : 0, dyb = (fy1.y != fy0.y) ? 1 : 0;
-                    if (PROJ) {
-                        f00 = make_float2(advect_global<PROJ>(a, F, P, y0a, x0a), advect_global<PROJ>(a, F, P, y0b, x0b));
-                        f01 = make_float2(advect_global<PROJ>(a, F, P, y0a, x0a + dxa), advect_global<PROJ>(a, F, P, y0b, x0b + dxb));
-                        f10 = make_float2(advect_global<PROJ>(a, F, P, y0a + dya, x0a), advect_global<PROJ>(a, F, P, y0b + dyb, x0b));
-                        f11 = make_float2(advect_global<PROJ>(a, F, P, y0a + dya, x0a + dxa), advect_global<PROJ>(a, F, P, y0b + dyb, x0b + dxb));
-                    } else {
-                        const float* qa = F + ((unsigned)y0a * pitch + x0a);
-                        const float* qb = F + ((unsigned)y0b * pitch + x0b);
-                        const int oya = dya * pitch, oyb = dyb * pitch;
-                        f00 = make_float2(__ldg(qa), __ldg(qb)); f01 = make_float2(__ldg(qa + dxa), __ldg(qb + dxb));
-                        f10 = make_float2(__ldg(qa + oya), __ldg(qb + oyb)); f11 = make_float2(__ldg(qa + oya + dxa), __ldg(qb + oyb + dxb));
-                    }
+                    gathered = true;
                 }
-            } else {
+            }
+            if (!gathered) {
                 fx1.x = fminf(fx1.x, xmax); fx1.y = fminf(fx1.y, xmax);
                 fy1.x = fminf(fy1.x, ymax); fy1.y = fminf(fy1.y, ymax);
                 const int dxa = (fx1.x != fx0.x) ? 1 : 0, dxb = (fx1.y != fx0.y) ? 1 : 0;
@@ -726,16 +714,19 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
                     if (y1b > rows - 1) dyb = 0;
                     y0a = clampi(y0a, 0, rows - 1); y0b = clampi(y0b, 0, rows - 1);
                 }
-                // both cells of the pair inside the staged window (with room for the +1 corners)?
-                const int lya = y0a - wy_org, lxa = x0a - wx_org, lyb = y0b - wy_org, lxb = x0b - wx_org;
+                // both cells of the pair inside the staged window?  (an interior tile comes here with a pair that is not, unless the
+                // slab clamp above just moved it back in)
                 bool inwin;
-                if (INTERIOR) inwin = ((unsigned)lya < (unsigned)(AT_FR - 1)) & ((unsigned)lxa < (unsigned)(AT_FP - 1)) &
-                                      ((unsigned)lyb < (unsigned)(AT_FR - 1)) & ((unsigned)lxb < (unsigned)(AT_FP - 1));
-                else inwin = y0a >= wy0 && y0a + dya < wy1 && x0a >= wx0 && x0a + dxa < wx1 &&
-                             y0b >= wy0 && y0b + dyb < wy1 && x0b >= wx0 && x0b + dxb < wx1;
+                if (INTERIOR && !SLAB) inwin = false;
+                else if (INTERIOR) {
+                    const int lya = y0a - wy_org, lxa = x0a - wx_org, lyb = y0b - wy_org, lxb = x0b - wx_org;
+                    inwin = ((unsigned)lya < (unsigned)(AT_FR - 1)) & ((unsigned)lxa < (unsigned)(AT_FP - 1)) &
+                            ((unsigned)lyb < (unsigned)(AT_FR - 1)) & ((unsigned)lxb < (unsigned)(AT_FP - 1));
+                } else inwin = y0a >= wy0 && y0a + dya < wy1 && x0a >= wx0 && x0a + dxa < wx1 &&
+                               y0b >= wy0 && y0b + dyb < wy1 && x0b >= wx0 && x0b + dxb < wx1;
                 if (inwin) {
-                    const float* qa = sF0 + (lya * AT_FP + lxa);
-                    const float* qb = sF0 + (lyb * AT_FP + lxb);
+                    const float* qa = sF0 + ((y0a - wy_org) * AT_FP + (x0a - wx_org));
+                    const float* qb = sF0 + ((y0b - wy_org) * AT_FP + (x0b - wx_org));
                     const int oya = dya * AT_FP, oyb = dyb * AT_FP;
                     f00 = make_float2(qa[0], qb[0]); f01 = make_float2(qa[dxa], qb[dxb]);
                     f10 = make_float2(qa[oya], qb[oyb]); f11 = make_float2(qa[oya + dxa], qb[oyb + dxb]);
@@ -826,6 +817,10 @@ k_advect_tiled(const AdvectArgs a)
                     j0 + AT_C - 1 <= a.w - 2 && gi_last <= h - 2 && j0 + AT_C <= a.cols && j0 + AT_C <= a.frame_pitch;
     // fused gradient subtract: the pressure window lies inside p, and every staged cell is one that k_project updates
     // (u rows 1 .. h-1: the window starts at row i0 - 4 >= 1; v columns 1 .. w-1: the window starts at column j0 - 4 >= 1)
+    // slab with a reach guard: the in-window gathers of an interior tile are not tested against the exact rows, so its window has to
+    // lie inside them (or its rows outside the guarded ones)
+    if (SLAB && a.overflow)
+        interior = interior && ((i0 - AT_HB >= a.valid_lo && i0 + AT_R + AT_HB <= a.valid_hi) || i0 + AT_R <= a.need_lo || i0 >= a.need_hi);
     if (PROJ) interior = interior && i0 >= AT_HB + 1 && i0 + AT_R + AT_HB <= a.h && j0 >= 8 && j0 + AT_C + 8 <= a.pc && j0 + AT_C + AT_HB <= a.w;
     if (interior) advect_tile<SLAB, true, PROJ>(a, T, sP, F, U, V, P, O, b, i0, j0);
     else          advect_tile<SLAB, false, PROJ>(a, T, sP, F, U, V, P, O, b, i0, j0);
