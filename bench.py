@@ -611,15 +611,19 @@ def run_slab(ctx, key, steps, warmup):
     host_d = torch.empty(own_rows, w, dtype=torch.float32).pin_memory()
     slab.step()                                   # eager once: NCCL / the peer mappings are set up on first use
 
+    ahead = not args.no_push_ahead
+
     def device_step(eager=False):
-        for _ in range(T):
-            slab.step()
+        if ahead:
+            slab.run_steps(T)               # every step but the last pushes the next step's ghost rows from its density advection
+        else:
+            for _ in range(T):
+                slab.step()
 
     def e2e_step():
         slab.setup_grid()
         slab.add_sources(ems)
-        for _ in range(T):
-            slab.step()
+        device_step()
         host_d.copy_(slab.owned("d"), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return host_d.unsqueeze(0)
@@ -635,7 +639,9 @@ def run_slab(ctx, key, steps, warmup):
     if world == 1:
         par = "single GPU, undecomposed; eager launches"
     else:
-        par = "row slabs over %d GPU(s), halo %d rows; %s; eager launches" % (world, slab.halo, slab.exchange_description())
+        par = "row slabs over %d GPU(s), halo %d rows; %s; %s; eager launches" % (
+            world, slab.halo, slab.exchange_description(),
+            "ghost rows of steps 2..%d pushed ahead from the previous step's density advection" % T if ahead else "every push at the head of its step")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -670,8 +676,11 @@ def slab_parity(ctx, slab, ems, h, w, K, Tj, nsteps=2):
     from smokephysai_b200 import NavierStokesSimulator
     slab.setup_grid()
     slab.add_sources(ems)
-    for _ in range(nsteps):
-        slab.step()
+    if ctx.args.no_push_ahead:
+        for _ in range(nsteps):
+            slab.step()
+    else:
+        slab.run_steps(nsteps)
     slab.check()
     got = {k: slab.gather(k) for k in ("u", "v", "p", "d")}
     res = None
@@ -709,6 +718,8 @@ def main():
     ap.add_argument("--sweeps-per-launch", type=int, default=0)
     ap.add_argument("--halo", type=int, default=0, help="c4: ghost rows per slab side (0: K + 4, one halo exchange per step; "
                     "sweeps-per-launch + 4 is the minimum and exchanges p after every Jacobi launch)")
+    ap.add_argument("--no-push-ahead", action="store_true", help="c4: every step pushes its ghost rows at its head (default: all but "
+                    "the first step of a bench step push them from the previous step's density advection: SlabNavierStokes.run_steps)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="c4 halo exchange: peer = direct stores into the neighbour's arena over NVLink (CUDA IPC), nccl = "
                          "ncclSend/ncclRecv groups issued from C, auto = peer when every neighbour is peer-accessible")

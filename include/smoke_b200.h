@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMK_ABI_VERSION 6
+#define SMK_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define SMK_API __attribute__((visibility("default")))
@@ -281,8 +281,14 @@ SMK_API int smk_peer_unpack(const smk_peer_comm_t* c, float* const* field_base_h
 /* One step() (navier_stokes.py:151-173) of a row slab in a single call: [peer exchange of u, v, density, p when comm != NULL],
  *     forces + diffusion + divergence, the Jacobi launches, gradient subtract, the three advections with their reach guards
  *     (chk_* may be NULL).  With comm the caller's halo must be at least jacobi_iters + 4 rows (one exchange per step).  comm == NULL
- *     steps a slab whose ghost rows the caller refreshed itself, or an undecomposed grid (gh == 0). */
-SMK_API int smk_slab_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, const smk_peer_comm_t* comm,
+ *     steps a slab whose ghost rows the caller refreshed itself, or an undecomposed grid (gh == 0).
+ *     flags (comm != NULL): SMK_SLAB_PUSH_HEAD -- push this rank's boundary rows at the head of the step (the plain exchange);
+ *     SMK_SLAB_PUSH_TAIL -- push the boundary rows the NEXT step needs from the middle of this step's density advection (the rows
+ *     to send are advected first), so that the transfer overlaps compute; the next call then omits SMK_SLAB_PUSH_HEAD.  All ranks
+ *     pass the same flags, and nothing may change the fields between a PUSH_TAIL step and the step that consumes it. */
+#define SMK_SLAB_PUSH_HEAD 1
+#define SMK_SLAB_PUSH_TAIL 2
+SMK_API int smk_slab_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, const smk_peer_comm_t* comm, int32_t flags,
                           const smk_slab_check_t* chk_u, const smk_slab_check_t* chk_v, const smk_slab_check_t* chk_d, void* stream);
 
 /*     the tail of that step alone: gradient subtract (:148-149) + advection of u, v, density (:166-168) + decay (:171) on the live

@@ -95,7 +95,7 @@ SIGNATURES = {
     "smk_ipc_close": [c_p, c_i64],
     "smk_peer_push": [C.POINTER(PeerComm), C.POINTER(c_p), c_p],
     "smk_peer_unpack": [C.POINTER(PeerComm), C.POINTER(c_p), c_p],
-    "smk_slab_step": [GP, SP, PP, C.POINTER(PeerComm), C.POINTER(SlabCheck), C.POINTER(SlabCheck), C.POINTER(SlabCheck), c_p],
+    "smk_slab_step": [GP, SP, PP, C.POINTER(PeerComm), c_i32, C.POINTER(SlabCheck), C.POINTER(SlabCheck), C.POINTER(SlabCheck), c_p],
     "smk_project_advect": [GP, SP, PP, C.POINTER(SlabCheck), C.POINTER(SlabCheck), C.POINTER(SlabCheck), c_p],
 }
 

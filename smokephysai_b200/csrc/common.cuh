@@ -96,6 +96,7 @@ struct EnvCfg {
     int fdd_bulk;        // SMK_FDD_BULK       0 / 1: staging path of k_forces_diffuse_div
     int advect_tiled;    // SMK_ADVECT_TILED   0 / 1: direct / shared-memory tiled advection
     int project_fused;   // SMK_PROJECT_FUSED  0: k_project + k_advect(u) as two kernels even where the fused one applies
+    int push_stream;     // SMK_PUSH_STREAM    0: the push a slab step issues for the next step stays on the caller's stream
 };
 const EnvCfg& env();
 
@@ -121,10 +122,16 @@ int launch_divergence(const smk_grid_t* g, const float* u, const float* v, float
 int launch_jacobi(const smk_grid_t* g, const float* div, float* p, float* scratch, int K, int T, int* in_scratch, cudaStream_t s);
 int launch_project(const smk_grid_t* g, const float* p, float* u, float* v, float dt, cudaStream_t s);
 int launch_bilerp(const float* f, int rows, int cols, int pitch, const float* y, const float* x, float* out, int64_t n, int mode, cudaStream_t s);
+// part (tiled kernel only, see advect_is_tiled): band_n > 0 -> only the tile rows [band_lo, band_lo + band_n); else every tile row
+// except those of the (up to two, ascending, disjoint) bands [skip_lo[k], skip_lo[k] + skip_n[k])
+struct AdvectPart { int band_lo, band_n, skip_lo[2], skip_n[2]; };
 int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows, int cols, int pitch, int64_t stride,
                   const float* u, const float* v, float dt, float scale, float* frame, int64_t frame_stride,
-                  const float* fmul, const smk_slab_check_t* chk, cudaStream_t s, int proj = 0, const float* p = nullptr, float* vout = nullptr);
+                  const float* fmul, const smk_slab_check_t* chk, cudaStream_t s, int proj = 0, const float* p = nullptr, float* vout = nullptr,
+                  const AdvectPart* part = nullptr);
 bool advect_can_fuse_project(const smk_grid_t* g);
+bool advect_is_tiled(const smk_grid_t* g, int rows, int cols);
+int advect_tile_rows();
 int launch_div_norms(const smk_grid_t* g, const float* u, const float* v, float* out, cudaStream_t s);
 int launch_jacobi_residual(const smk_grid_t* g, const float* div, const float* p, float* out, cudaStream_t s);
 int launch_fractal_fields(float* perlin, float* mandel, float* mul, int na, int nb, int pitch, float intensity, int iterations,

@@ -155,6 +155,31 @@ static int peer_xfer(const smk_peer_comm_t* c, float* const* base, bool push, cu
     return check_launch(push ? "k_halo_push" : "k_halo_unpack");
 }
 
+// The push a step issues for the NEXT step (SMK_SLAB_PUSH_TAIL) runs on a stream of its own, next to the rest of the density
+// advection: forked from the caller's stream after the boundary bands (ev_fork), joined at the head of the next step (ev_join,
+// which also keeps the push's reads of p ahead of that step's Jacobi launches).  One set per device; highest stream priority, so
+// the push's CTAs are placed as soon as CTAs of the advection retire.
+struct SideStream { cudaStream_t s; cudaEvent_t ev_fork, ev_join; bool ok, pending; };
+static SideStream* side_stream()
+{
+    static SideStream side[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream& x = side[dev];
+    if (!x.ok) {
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { lo = hi = 0; }
+        if (cudaStreamCreateWithPriority(&x.s, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&x.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&x.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        x.ok = true;
+    }
+    return &x;
+}
+
 typedef CUresult (*hx_range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
 static hx_range_fn hx_range()
 {
@@ -174,29 +199,84 @@ using namespace smk;
 
 #define SMK_TRY_(x) do { const int rc_ = (x); if (rc_ != SMK_OK) return rc_; } while (0)
 
+// The density advection of a step, optionally with the NEXT step's halo push issued from the middle of it (push_comm != NULL):
+// the tile rows that hold the rows this rank sends to its neighbours are advected first (two short launches), then k_halo_push
+// copies the boundary rows of the new u, v, density and of p into the neighbours' mailboxes, then the rest of the field is
+// advected -- the NVLink transfer, the counters' flight and the neighbours' skew hide behind that last launch and the
+// neighbour's own, instead of heading the next step.  new_base: the live u, v, density, p once this step is complete.
+static int advect_density(const smk_grid_t* g, const float* d_in, float* d_out, const float* u, const float* v, const smk_params_t* prm,
+                          const smk_slab_check_t* chk_d, cudaStream_t s, const smk_peer_comm_t* push_comm, float* const* new_base)
+{
+    if (!push_comm)
+        return launch_advect(g, d_in, d_out, g->h, g->w, g->pitch_c, 0, u, v, prm->dt, prm->decay, nullptr, 0, nullptr, chk_d, s);
+    AdvectPart rest = {0, 0, {0, 0}, {0, 0}};
+    int nb = 0;
+    if (advect_is_tiled(g, g->h, g->w)) {
+        const int TR = advect_tile_rows(), nty = (g->h + TR - 1) / TR;
+        int lo[2], hi[2];
+        for (int l = 0; l < 2; ++l) {
+            const smk_peer_link_t& k = push_comm->link[l];
+            if (!k.remote_mailbox || k.send_count[2] <= 0) continue;
+            const int64_t r0 = k.send_off[2] / g->pitch_c, r1 = (k.send_off[2] + k.send_count[2] + g->pitch_c - 1) / g->pitch_c;
+            int a = (int)(r0 / TR), b = (int)((r1 + TR - 1) / TR);
+            a = a < 0 ? 0 : a; b = b > nty ? nty : b;
+            if (a >= b) continue;
+            lo[nb] = a; hi[nb] = b; ++nb;
+        }
+        if (nb == 2 && lo[1] < lo[0]) { int t = lo[0]; lo[0] = lo[1]; lo[1] = t; t = hi[0]; hi[0] = hi[1]; hi[1] = t; }
+        if (nb == 2 && lo[1] < hi[0]) { hi[0] = hi[0] > hi[1] ? hi[0] : hi[1]; nb = 1; }          // overlapping bands: one
+        for (int k = 0; k < nb; ++k) {
+            const AdvectPart band = {lo[k], hi[k] - lo[k], {0, 0}, {0, 0}};
+            SMK_TRY_(launch_advect(g, d_in, d_out, g->h, g->w, g->pitch_c, 0, u, v, prm->dt, prm->decay, nullptr, 0, nullptr, chk_d, s,
+                                   0, nullptr, nullptr, &band));
+            rest.skip_lo[k] = lo[k]; rest.skip_n[k] = hi[k] - lo[k];
+        }
+    }
+    if (nb == 0) {
+        // small field (direct kernel) or nothing to send: advect everything, then push
+        SMK_TRY_(launch_advect(g, d_in, d_out, g->h, g->w, g->pitch_c, 0, u, v, prm->dt, prm->decay, nullptr, 0, nullptr, chk_d, s));
+        return peer_xfer(push_comm, new_base, true, s);
+    }
+    // the push on the side stream (after the bands), the rest of the advection on the caller's; SMK_PUSH_STREAM=0: one stream
+    SideStream* side = env().push_stream == 0 ? nullptr : side_stream();
+    if (side && cudaEventRecord(side->ev_fork, s) == cudaSuccess && cudaStreamWaitEvent(side->s, side->ev_fork, 0) == cudaSuccess) {
+        SMK_TRY_(peer_xfer(push_comm, new_base, true, side->s));
+        if (cudaEventRecord(side->ev_join, side->s) != cudaSuccess) return fail(SMK_EINVAL, "smk_slab_step: cudaEventRecord failed: %s", cudaGetErrorString(cudaGetLastError()));
+        side->pending = true;
+    } else {
+        (void)cudaGetLastError();
+        SMK_TRY_(peer_xfer(push_comm, new_base, true, s));
+    }
+    return launch_advect(g, d_in, d_out, g->h, g->w, g->pitch_c, 0, u, v, prm->dt, prm->decay, nullptr, 0, nullptr, chk_d, s,
+                         0, nullptr, nullptr, &rest);
+}
+
 // The tail of a step on a (slab) grid whose live u, v, density are the outputs of forces + diffusion and whose live p holds the
 // K sweeps: gradient subtract (navier_stokes.py:148-149), sequential advection of u, v, density (:166-168), decay (:171).
 // The live copies of u and density flip; so does v's, except on big fields, where the gradient subtract runs inside the u
 // advection (k_advect_tiled<.., 1>, stencil.cu), the projected v passes through the spare copy and the live v ends where it was.
 static int project_advect(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
-                          const smk_slab_check_t* chk_u, const smk_slab_check_t* chk_v, const smk_slab_check_t* chk_d, cudaStream_t s)
+                          const smk_slab_check_t* chk_u, const smk_slab_check_t* chk_v, const smk_slab_check_t* chk_d, cudaStream_t s,
+                          const smk_peer_comm_t* push_comm = nullptr)
 {
     const int cu = st->cur_u, cv = st->cur_v, cd = st->cur_d;
     float *u1 = st->u[cu], *u0 = st->u[cu ^ 1], *v1 = st->v[cv], *v0 = st->v[cv ^ 1], *d1 = st->d[cd], *d0 = st->d[cd ^ 1];
-    const float* pl = st->p[st->cur_p];
+    float* pl = st->p[st->cur_p];
     if (advect_can_fuse_project(g)) {
         // u advection with the gradient subtract inside; it leaves the projected v in the spare copy v0, so the v advection runs
         // v0 -> v1 and the live v stays in the copy it was in
         SMK_TRY_(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, 0, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, chk_u, s, 1, pl, v0));
         SMK_TRY_(launch_advect(g, v0, v1, g->h, g->w + 1, g->pitch_v, 0, u0, v0, prm->dt, 1.0f, nullptr, 0, nullptr, chk_v, s));
-        SMK_TRY_(launch_advect(g, d1, d0, g->h, g->w, g->pitch_c, 0, u0, v1, prm->dt, prm->decay, nullptr, 0, nullptr, chk_d, s));
+        float* nb_[4] = {u0, v1, d0, pl};
+        SMK_TRY_(advect_density(g, d1, d0, u0, v1, prm, chk_d, s, push_comm, nb_));
         st->cur_u = cu ^ 1; st->cur_d = cd ^ 1;
         return SMK_OK;
     }
     SMK_TRY_(launch_project(g, pl, u1, v1, prm->dt, s));
     SMK_TRY_(launch_advect(g, u1, u0, g->h + 1, g->w, g->pitch_u, 0, u1, v1, prm->dt, 1.0f, nullptr, 0, nullptr, chk_u, s));
     SMK_TRY_(launch_advect(g, v1, v0, g->h, g->w + 1, g->pitch_v, 0, u0, v1, prm->dt, 1.0f, nullptr, 0, nullptr, chk_v, s));
-    SMK_TRY_(launch_advect(g, d1, d0, g->h, g->w, g->pitch_c, 0, u0, v0, prm->dt, prm->decay, nullptr, 0, nullptr, chk_d, s));
+    float* nb_[4] = {u0, v0, d0, pl};
+    SMK_TRY_(advect_density(g, d1, d0, u0, v0, prm, chk_d, s, push_comm, nb_));
     st->cur_u = cu ^ 1; st->cur_v = cv ^ 1; st->cur_d = cd ^ 1;
     return SMK_OK;
 }
@@ -261,7 +341,7 @@ int smk_peer_unpack(const smk_peer_comm_t* c, float* const* field_base_host, voi
     return peer_xfer(c, field_base_host, false, (cudaStream_t)stream);
 }
 
-int smk_slab_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, const smk_peer_comm_t* comm,
+int smk_slab_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm, const smk_peer_comm_t* comm, int32_t flags,
                   const smk_slab_check_t* chk_u, const smk_slab_check_t* chk_v, const smk_slab_check_t* chk_d, void* stream)
 {
     SMK_TRY(check_grid(g, "smk_slab_step"));
@@ -276,9 +356,17 @@ int smk_slab_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
         if (c && (!c->overflow_flag || c->need_lo > c->need_hi || c->valid_lo > c->valid_hi)) return fail(SMK_EINVAL, "smk_slab_step: bad check ranges");
     cudaStream_t s = (cudaStream_t)stream;
     // 0. ghost rows of the live u, v, density, p from both neighbours (one exchange per step: the caller's halo is >= K + 4 rows)
+    //    SMK_SLAB_PUSH_HEAD: this rank's rows are pushed here; without it the previous step already pushed them from its tail
+    if (flags & ~(SMK_SLAB_PUSH_HEAD | SMK_SLAB_PUSH_TAIL)) return fail(SMK_EINVAL, "smk_slab_step: unknown flags 0x%x", (unsigned)flags);
     if (comm) {
+        // join the push the previous step left on the side stream (if any)
+        SideStream* side = side_stream();
+        if (side && side->pending) {
+            side->pending = false;
+            if (cudaStreamWaitEvent(s, side->ev_join, 0) != cudaSuccess) return fail(SMK_EINVAL, "smk_slab_step: cudaStreamWaitEvent failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
         float* base[4] = {st->u[st->cur_u], st->v[st->cur_v], st->d[st->cur_d], st->p[st->cur_p]};
-        SMK_TRY(peer_xfer(comm, base, true, s));
+        if (flags & SMK_SLAB_PUSH_HEAD) SMK_TRY(peer_xfer(comm, base, true, s));
         SMK_TRY(peer_xfer(comm, base, false, s));
     }
     const int cu = st->cur_u, cv = st->cur_v, cd = st->cur_d;
@@ -291,7 +379,8 @@ int smk_slab_step(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,
     SMK_TRY(launch_jacobi(g, st->div, st->p[st->cur_p], st->p[st->cur_p ^ 1], prm->jacobi_iters, prm->sweeps_per_launch, &flip, s));
     st->cur_p ^= flip;
     // 4-5. gradient subtract + the three advections + decay                    :148-149, :166-171
-    return project_advect(g, st, prm, chk_u, chk_v, chk_d, s);
+    //    SMK_SLAB_PUSH_TAIL: the ghost rows of the NEXT step leave from the middle of the density advection
+    return project_advect(g, st, prm, chk_u, chk_v, chk_d, s, (comm && (flags & SMK_SLAB_PUSH_TAIL)) ? comm : nullptr);
 }
 
 int smk_project_advect(const smk_grid_t* g, smk_state_t* st, const smk_params_t* prm,

@@ -383,6 +383,9 @@ struct AdvectArgs {
     int need_lo, need_hi, valid_lo, valid_hi; int* overflow;
     const float* P; int pc; long long sc_;               // k_advect_tiled<.., 1>: pressure for the fused gradient subtract,
     float* Vout;                                         // and where the projected v goes (a different array than V)
+    // k_advect_tiled on a part of the tile rows (smk_slab_step computes the rows it sends to its neighbours first): the launch
+    // covers tile rows ty0 + blockIdx.y, stepping over the rows [skip_lo[k], skip_lo[k] + skip_n[k]) of up to two bands
+    int ty0, skip_lo[2], skip_n[2];
 };
 
 template <bool SLAB>
@@ -797,7 +800,10 @@ k_advect_tiled(const AdvectArgs a)
     __shared__ __align__(16) typename std::conditional<PROJ != 0, AdvectTileP, AdvectTile>::type TT;
     AdvectTile& T = *reinterpret_cast<AdvectTile*>(&TT);
     float (*sP)[AT_PP] = PROJ ? reinterpret_cast<float (*)[AT_PP]>(reinterpret_cast<char*>(&TT) + sizeof(AdvectTile)) : nullptr;
-    const int i0 = blockIdx.y * AT_R, j0 = blockIdx.x * AT_C;
+    int ty = (int)blockIdx.y + a.ty0;
+    if (ty >= a.skip_lo[0]) ty += a.skip_n[0];
+    if (ty >= a.skip_lo[1]) ty += a.skip_n[1];
+    const int i0 = ty * AT_R, j0 = blockIdx.x * AT_C;
     const size_t b = blockIdx.z;
     const float* F = a.F + b * a.stride;
     const float* U = a.U + b * a.su_;
@@ -838,9 +844,20 @@ bool advect_can_fuse_project(const smk_grid_t* g)
     return (tiled == 1 || (tiled == -1 && big) || forced) && (g->h + 1 + AT_R - 1) / AT_R <= 65535;
 }
 
+// true when launch_advect (without a fused gradient subtract) would run k_advect_tiled for a field of this size
+bool advect_is_tiled(const smk_grid_t* g, int rows, int cols)
+{
+    int tiled = -1;
+    if (env().advect_tiled != SMK_ENV_UNSET) tiled = env().advect_tiled;
+    const bool big = (int64_t)rows * cols * g->batch >= (int64_t)6 << 20;
+    return (tiled == 1 || (tiled == -1 && big)) && (rows + AT_R - 1) / AT_R <= 65535;
+}
+int advect_tile_rows() { return AT_R; }
+
 int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows, int cols, int pitch, int64_t stride,
                   const float* u, const float* v, float dt, float scale, float* frame, int64_t frame_stride,
-                  const float* fmul, const smk_slab_check_t* chk, cudaStream_t s, int proj, const float* p, float* vout)
+                  const float* fmul, const smk_slab_check_t* chk, cudaStream_t s, int proj, const float* p, float* vout,
+                  const AdvectPart* part)
 {
     if ((int64_t)rows * pitch >= (1ll << 31)) return fail(SMK_EUNSUPPORTED, "smk_advect: field of %d x %d exceeds 2^31 elements", rows, pitch);
     AdvectArgs a;
@@ -855,6 +872,7 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
     a.need_lo = chk ? chk->need_lo : 0; a.need_hi = chk ? chk->need_hi : 0;
     a.valid_lo = chk ? chk->valid_lo : 0; a.valid_hi = chk ? chk->valid_hi : 0; a.overflow = chk ? chk->overflow_flag : nullptr;
     a.P = p; a.pc = g->pitch_c; a.sc_ = g->stride_c; a.Vout = vout;
+    a.ty0 = 0; a.skip_lo[0] = a.skip_lo[1] = 0x7fffffff; a.skip_n[0] = a.skip_n[1] = 0;
     const unsigned long long nthreads = (unsigned long long)rows * a.ngroups;
     dim3 grid((unsigned)((nthreads + 255) / 256), g->batch);
     if (proj) {
@@ -875,10 +893,21 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
     const bool big = (int64_t)rows * cols * g->batch >= (int64_t)6 << 20;
     if ((tiled == 1 || (tiled == -1 && big)) && (rows + AT_R - 1) / AT_R <= 65535) {
         dim3 tgrid((unsigned)((pitch + AT_C - 1) / AT_C), (unsigned)((rows + AT_R - 1) / AT_R), g->batch);
+        if (part) {
+            // a band of tile rows, or everything but up to two bands
+            int ny = (int)tgrid.y;
+            if (part->band_n > 0) { a.ty0 = part->band_lo; ny = part->band_n; }
+            else
+                for (int k = 0; k < 2; ++k)
+                    if (part->skip_n[k] > 0) { a.skip_lo[k] = part->skip_lo[k]; a.skip_n[k] = part->skip_n[k]; ny -= part->skip_n[k]; }
+            if (ny <= 0) return SMK_OK;
+            tgrid.y = (unsigned)ny;
+        }
         if (slab) launch_chain(k_advect_tiled<true, 0>, tgrid, dim3(256), 0, s, a);
         else      launch_chain(k_advect_tiled<false, 0>, tgrid, dim3(256), 0, s, a);
         return check_launch("k_advect_tiled");
     }
+    if (part) return fail(SMK_EUNSUPPORTED, "launch_advect: a part of the rows needs the tiled kernel (advect_is_tiled)");
     if (slab) launch_chain(k_advect<true>, grid, dim3(256), 0, s, a);
     else      launch_chain(k_advect<false>, grid, dim3(256), 0, s, a);
     return check_launch("k_advect");

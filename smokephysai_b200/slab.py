@@ -449,6 +449,7 @@ class SlabNavierStokes:
                 self.exchanger = NcclExchanger(self.local._cuda)
         self._overflow = torch.zeros(1, dtype=torch.int32, device=self.local._cuda)
         self.steps_done = 0
+        self._pushed_ahead = False          # the last step already pushed the ghost rows of the next one (step(push_ahead=True))
 
     # ------------------------------------------------------------------ fields
     def full(self, name):
@@ -470,8 +471,14 @@ class SlabNavierStokes:
         cols = {"u": self.geom.W, "v": self.geom.W + 1}.get(name, self.geom.W)
         return self.full(name)[lo:hi, :cols]
 
+    def _no_push_in_flight(self, what):
+        if self._pushed_ahead:
+            raise RuntimeError("%s after step(push_ahead=True): the boundary rows of the next step are already on their way to the "
+                               "neighbours; finish with a plain step() first (run_steps does)" % what)
+
     def scatter(self, name, global_field):
         """Fill the stored rows (owned + ghosts) of a field from the global [rows, cols] array."""
+        self._no_push_in_flight("scatter")
         g = torch.as_tensor(global_field, dtype=torch.float32)
         rows = self.geom.rows(self._kind(name))
         dst = self.full(name)
@@ -479,13 +486,16 @@ class SlabNavierStokes:
 
     def add_smoke_source(self, x, y, radius=10, intensity=1.0):
         """navier_stokes.py:37-48 with the centre given in global coordinates."""
+        self._no_push_in_flight("add_smoke_source")
         self.local.add_smoke_source(x, int(y) - self.geom.A, radius, intensity)
 
     def add_sources(self, sources):
         """Ordered emitter list [(x, y, radius, intensity), ...] in global coordinates, one batched splat."""
+        self._no_push_in_flight("add_sources")
         self.local.add_sources([[(x, int(y) - self.geom.A, r, i) for x, y, r, i in sources]])
 
     def setup_grid(self):
+        self._no_push_in_flight("setup_grid")
         self.local.setup_grid()
         self._overflow.zero_()
 
@@ -542,7 +552,9 @@ class SlabNavierStokes:
         else:
             self.exchanger.exchange(self.geom, self.exchange_list(names))
 
-    def _c_step(self):
+    PUSH_HEAD, PUSH_TAIL = 1, 2             # SMK_SLAB_PUSH_* of include/smoke_b200.h
+
+    def _c_step(self, flags=1):
         """The whole step in one C call (smk_slab_step): peer exchange, forces / diffusion / divergence, Jacobi launches,
         gradient subtract, the three advections.  Same kernels, same order as the plan below."""
         ns, g = self.local, self.geom
@@ -550,22 +562,37 @@ class SlabNavierStokes:
         chk = [self._check(rows) for rows in (g.hl + 1, g.hl, g.hl)]
         ref = [C.byref(c) if c is not None else None for c in chk]
         comm = C.byref(self.exchanger.comm) if isinstance(self.exchanger, PeerExchanger) else None
-        _lib.call("smk_slab_step", self._g(), C.byref(ns._state), C.byref(prm), comm, ref[0], ref[1], ref[2], ns._stream())
+        _lib.call("smk_slab_step", self._g(), C.byref(ns._state), C.byref(prm), comm, int(flags), ref[0], ref[1], ref[2], ns._stream())
         self.steps_done += 1
 
-    def step(self):
-        """One time step of this rank's slab (all ranks must call it together)."""
+    def step(self, push_ahead=False):
+        """One time step of this rank's slab (all ranks must call it together, with the same arguments).
+
+        push_ahead=True (peer-store exchange with one exchange per step; ignored otherwise) promises that the next thing to happen
+        to this slab is another step(): the boundary rows that step needs are then sent from the middle of this step's density
+        advection (the rows to send are advected first), and the transfer overlaps the rest of the launch instead of heading the
+        next step.  run_steps(n) does this for all but the last step."""
         if self.world == 1 or (self.single_exchange and self.exchanger and not getattr(self, "_phase_by_phase", False)):
             # one exchange per step: the compute part is ONE C call (smk_slab_step), which also issues the exchange when it
             # is the peer-store one; an NCCL / torch.distributed exchange is issued from here first
-            if self.world > 1 and not isinstance(self.exchanger, PeerExchanger):
+            peer = self.world > 1 and isinstance(self.exchanger, PeerExchanger)
+            if self.world > 1 and not peer:
                 self.exchange(("u", "v", "d", "p"))
-            return self._c_step()
+            flags = 0
+            if peer:
+                flags = (0 if self._pushed_ahead else self.PUSH_HEAD) | (self.PUSH_TAIL if push_ahead else 0)
+                self._pushed_ahead = bool(push_ahead)
+            return self._c_step(flags)
         for kind, arg in self.step_plan():
             if kind == "x":
                 self.exchange(arg)
             else:
                 arg()
+
+    def run_steps(self, nsteps):
+        """nsteps consecutive steps; every step but the last sends the next step's ghost rows ahead (step(push_ahead=True))."""
+        for k in range(int(nsteps)):
+            self.step(push_ahead=k + 1 < int(nsteps))
 
     def exchange_description(self):
         """One line for logs / bench output: how the ghost rows travel."""
@@ -589,8 +616,7 @@ class SlabNavierStokes:
         torch.cuda.synchronize(ns._cuda)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            for _ in range(int(nsteps)):
-                self.step()
+            self.run_steps(nsteps)
         after = (st.cur_u, st.cur_v, st.cur_d, st.cur_p)
         if after != before:
             raise RuntimeError("the ping-pong state does not return to the same buffers after %d step(s): capture an even number" % nsteps)
@@ -666,6 +692,22 @@ class LocalGroup:
             else:
                 for p in plans:
                     p[k][1]()
+
+    def run_steps(self, nsteps):
+        """nsteps steps through smk_slab_step with the ghost rows of every step but the first pushed ahead from the previous step's
+        density advection (SlabNavierStokes.run_steps on one GPU).  Everything runs on one stream, so a kernel that waits for a push
+        must be queued after it: the first step's pushes of ALL slabs are issued up front, and every step's tail pushes are queued
+        before the next step's unpacks because the slabs are walked step by step."""
+        if not (self.peer and all(s.single_exchange for s in self.slabs)):
+            for _ in range(int(nsteps)):
+                self.step()
+            return
+        names = ("u", "v", "d", "p")
+        for s in self.slabs:
+            s.exchanger.push([(s.full(n), n) for n in names])
+        for k in range(int(nsteps)):
+            for s in self.slabs:
+                s._c_step(SlabNavierStokes.PUSH_TAIL if k + 1 < int(nsteps) else 0)
 
     def gather(self, name):
         self.check()

@@ -47,7 +47,7 @@ def test_ctypes_table_matches_header(so_path):
         assert len(args) == decl[name], "%s: %d ctypes args vs %d in the header" % (name, len(args), decl[name])
     lib = _lib.load()
     want = int(re.search(r"#define SMK_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
-    assert lib.smk_version() == want == 6
+    assert lib.smk_version() == want == 7
     assert isinstance(lib.smk_last_error_string(), bytes)
 
 

@@ -102,16 +102,22 @@ def _nccl_worker(rank, world, port, H, W, K, T, steps, out_dir, exch):
     try:
         st0 = random_state(H, W, seed=21)
         from smokephysai_b200.slab import DistExchanger, NcclExchanger, PeerExchanger
-        halo = K + 6 if exch == "peer-one-call" else None
+        halo = K + 6 if exch.startswith("peer-one-call") else None
         slab = SlabNavierStokes((H, W), 0.02, 0.01, "cuda:%d" % rank, rank=rank, world=world, jacobi_iters=K, sweeps_per_launch=T, halo=halo,
                                 exchanger=DistExchanger() if exch == "torch" else None,
                                 exchange="peer" if exch.startswith("peer") else "nccl")
         assert isinstance(slab.exchanger, {"torch": DistExchanger, "library": NcclExchanger}.get(exch, PeerExchanger))
-        assert slab.single_exchange == (exch == "peer-one-call")
+        assert slab.single_exchange == exch.startswith("peer-one-call")
         for k in ("u", "v", "p", "d"):
             slab.scatter(k, st0[k])
-        for _ in range(steps):
-            slab.step()
+        if exch == "peer-one-call-ahead":
+            os.environ["SMK_ADVECT_TILED"] = "1"          # the banded density advection with the push in its middle
+            _lib.reload_env()
+            slab.run_steps(steps - 1)
+            slab.step()                                   # a head push again after a run that ended without a tail push
+        else:
+            for _ in range(steps):
+                slab.step()
         slab.check()
         full = {k: slab.gather(k).cpu().numpy() for k in ("u", "v", "p", "d")}
         if rank == 0:
@@ -124,7 +130,7 @@ def _nccl_worker(rank, world, port, H, W, K, T, steps, out_dir, exch):
 
 
 @pytest.mark.timeout(150)
-@pytest.mark.parametrize("exch", ["library", "torch", "peer", "peer-one-call"])
+@pytest.mark.parametrize("exch", ["library", "torch", "peer", "peer-one-call", "peer-one-call-ahead"])
 def test_nccl_slabs_match_undecomposed(tmp_path, exch):
     """Real NVLink: halo exchange through the library's own NCCL communicator (smk_nccl_exchange), through torch.distributed
     P2P ops, and by direct peer stores into IPC-mapped mailboxes (smk_peer_push / smk_peer_unpack; "peer-one-call": deep halo,
@@ -133,7 +139,7 @@ def test_nccl_slabs_match_undecomposed(tmp_path, exch):
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     import torch.multiprocessing as mp
-    H, W, K, T, steps = 512, 384, 20, 10, 3
+    H, W, K, T, steps = 512, 384, 20, 10, (5 if exch == "peer-one-call-ahead" else 3)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_nccl_worker, args=(world, port, H, W, K, T, steps, str(tmp_path), exch), nprocs=world, join=True)
     st0 = random_state(H, W, seed=21)
@@ -200,6 +206,56 @@ def test_peer_exchange_kernels_on_one_gpu(world, H, W, K, T, halo):
     # the counters moved in lockstep: every slab completed the same number of exchanges
     seqs = {int(s.exchanger.buf[-PeerSeqOffset:].view(torch.int32)[2].item()) for s in grp.slabs}
     assert len(seqs) == 1 and seqs.pop() > 0
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("tiled,side", [(0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("world,H,W,K,halo", [(2, 200, 132, 8, 14), (3, 300, 260, 12, 18), (4, 512, 384, 20, 26), (8, 1024, 200, 20, 26)])
+def test_ghost_rows_pushed_ahead_from_the_density_advection(world, H, W, K, halo, tiled, side):
+    """smk_slab_step with SMK_SLAB_PUSH_TAIL: the tile rows holding the rows a slab sends are advected first, the push for the NEXT
+    step leaves between them and the rest of the density advection, and the next step starts with the unpack alone.  Tiled
+    advection (bands, merged where a slab is only a few tiles tall) and the direct kernel (push after the whole launch), over enough
+    steps for both mailbox slots to be reused, against the undecomposed run bit for bit; then two more plain steps on the same
+    slabs (a head push after a run that ended without a tail push).  side: the push on the library's high-priority side stream
+    (default) or on the caller's stream (SMK_PUSH_STREAM=0)."""
+    from helpers import smk_env
+    st0 = random_state(H, W, seed=70 + world)
+    with smk_env(SMK_ADVECT_TILED=tiled, SMK_PUSH_STREAM=side):
+        grp = LocalGroup((H, W), 0.02, 0.01, "cuda", world=world, jacobi_iters=K, sweeps_per_launch=max(K // 2, 1), halo=halo, peer=True)
+        assert all(s.single_exchange for s in grp.slabs)
+        whole = NavierStokesSimulator((H, W), 0.02, 0.01, "cuda", jacobi_iters=K, step_kernel="phases")
+        for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+            grp.scatter(k, st0[k])
+            setattr(whole, name, torch.from_numpy(st0[k]).cuda())
+        _lib.profile_begin(max_records=4096)
+        grp.run_steps(5)
+        torch.cuda.synchronize()
+        prof = _lib.profile_end()
+        for _ in range(5):
+            whole.step()
+        grp.check()
+        for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+            ref = N(getattr(whole, name))
+            assert_same(N(grp.gather(k))[:, :ref.shape[1]], ref, "%s, pushed ahead, world %d, tiled %d" % (k, world, tiled))
+        # one push and one unpack per slab and step; with the tiled kernel the density advection of a push-ahead step is
+        # bands + rest (2 or 3 launches) instead of 1
+        assert prof["halo"][1] == 5 * world and prof["halo_unpack"][1] == 5 * world
+        assert prof["advect_d"][1] == 5 * world if not tiled else prof["advect_d"][1] >= 4 * world * 2 + world
+        grp.run_steps(2)
+        for _ in range(2):
+            whole.step()
+        for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+            ref = N(getattr(whole, name))
+            assert_same(N(grp.gather(k))[:, :ref.shape[1]], ref, "%s, second run, world %d, tiled %d" % (k, world, tiled))
+
+
+def test_fields_cannot_change_while_a_push_is_in_flight():
+    a = SlabNavierStokes((300, 260), 0.02, 0.01, "cuda", rank=0, world=1, jacobi_iters=12, sweeps_per_launch=6)
+    a._pushed_ahead = True
+    for call in (lambda: a.add_smoke_source(10, 10), lambda: a.add_sources([(10, 10, 3, 1.0)]), a.setup_grid,
+                 lambda: a.scatter("u", np.zeros((301, 260), np.float32))):
+        with pytest.raises(RuntimeError, match="push_ahead"):
+            call()
 
 
 def test_slab_step_in_one_c_call_equals_the_phase_calls():
