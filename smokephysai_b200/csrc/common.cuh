@@ -97,6 +97,7 @@ struct EnvCfg {
     int advect_tiled;    // SMK_ADVECT_TILED   0 / 1: direct / shared-memory tiled advection
     int project_fused;   // SMK_PROJECT_FUSED  0: k_project + k_advect(u) as two kernels even where the fused one applies
     int push_stream;     // SMK_PUSH_STREAM    0: the push a slab step issues for the next step stays on the caller's stream
+    int splat_big;       // SMK_SPLAT_BIG      0 / 1: k_splat / k_splat_big (128 x 64 cells per CTA) whatever the grid size
 };
 const EnvCfg& env();
 

@@ -965,10 +965,97 @@ k_splat(float* __restrict__ Dn, const int h, const int w, const int pc, const lo
     if (in) *cell = acc;
 }
 
+// The same for big grids with long emitter lists (8192 x 8192 carries 16 k emitters): every CTA of k_splat culls the WHOLE list, so
+// its cost is (number of CTAs) x (list length) -- 10.2 ms at 8192^2, six steps' worth of kernels (profiles/r02q_launches_c4*).  Here
+// a CTA owns 128 x 64 cells, 32 per thread, i.e. 32 x fewer passes over the list; a listed emitter is loaded once per thread and
+// tested against the thread's 32 cells.  Every cell still adds its emitters in list order with the same operations: bit-identical.
+constexpr int SPB_W = 128, SPB_H = 64;
+__global__ void __launch_bounds__(256)
+k_splat_big(float* __restrict__ Dn, const int h, const int w, const int pc, const long long sc_,
+            const smk_source_t* __restrict__ src, const int32_t* __restrict__ off)
+{
+    __shared__ int list[256];
+    __shared__ int wcount[8];
+    const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x, wp = threadIdx.y;
+    const int j0 = blockIdx.x * SPB_W, i0 = blockIdx.y * SPB_H;
+    const int b = blockIdx.z;
+    const int s0 = off[b], s1 = off[b + 1];
+    if (s0 == s1) return;
+    float* base_ = Dn + (size_t)b * sc_;
+    float acc[SPB_H / 8][SPB_W / 32];
+    bool any = false;
+    for (int base = s0; base < s1; base += 256) {
+        const int k = base + tid;
+        bool hit = false;
+        if (k < s1) {
+            const smk_source_t e = src[k];
+            const long long r = e.radius;
+            hit = (long long)j0 <= e.x + r && (long long)j0 + (SPB_W - 1) >= e.x - r && (long long)i0 <= e.y + r && (long long)i0 + (SPB_H - 1) >= e.y - r;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) wcount[wp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { if (q < wp) before += wcount[q]; total += wcount[q]; }
+        if (hit) list[before + __popc(m & ((1u << lane) - 1u))] = k;
+        __syncthreads();
+        if (total > 0 && !any) {                                              // first emitter that touches the tile: load the cells
+            any = true;
+#pragma unroll
+            for (int cy = 0; cy < SPB_H / 8; ++cy)
+#pragma unroll
+                for (int cx = 0; cx < SPB_W / 32; ++cx) {
+                    const int i = i0 + wp + 8 * cy, j = j0 + lane + 32 * cx;
+                    acc[cy][cx] = (i < h && j < w) ? base_[(size_t)i * pc + j] : 0.f;
+                }
+        }
+        for (int q = 0; q < total; ++q) {
+            const smk_source_t e = src[list[q]];
+            const float rad = (float)e.radius;
+            const double r3 = (double)e.radius / 3.0;
+            const float denom = (float)(2.0 * (r3 * r3));
+#pragma unroll
+            for (int cy = 0; cy < SPB_H / 8; ++cy) {
+                const long long dy = (long long)(i0 + wp + 8 * cy) - e.y;
+#pragma unroll
+                for (int cx = 0; cx < SPB_W / 32; ++cx) {
+                    const long long dx = (long long)(j0 + lane + 32 * cx) - e.x;
+                    const float dist = sqrtf((float)(dx * dx + dy * dy));    // navier_stokes.py:45
+                    if (dist <= rad) {                                       // :46
+                        const float d2 = dist * dist;
+                        acc[cy][cx] = acc[cy][cx] + e.intensity * expf((-d2) / denom);      // :48
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (any) {
+#pragma unroll
+        for (int cy = 0; cy < SPB_H / 8; ++cy)
+#pragma unroll
+            for (int cx = 0; cx < SPB_W / 32; ++cx) {
+                const int i = i0 + wp + 8 * cy, j = j0 + lane + 32 * cx;
+                if (i < h && j < w) base_[(size_t)i * pc + j] = acc[cy][cx];
+            }
+    }
+}
+
 int launch_splat(const smk_grid_t* g, float* density, const smk_source_t* src, const int32_t* off, cudaStream_t s)
 {
-    dim3 grid((g->w + 31) / 32, (g->h + 7) / 8, g->batch), blk(32, 8);
     ProfScope prof_(SMK_PH_SPLAT, s);
+    // big grids (their lists are long: one emitter per 64 x 64 block in the benches) take the big-tile kernel; SMK_SPLAT_BIG = 0 / 1 forces
+    const int forced = env().splat_big;
+    const bool big = forced != SMK_ENV_UNSET ? forced != 0 : (int64_t)g->h * g->w >= ((int64_t)4 << 20);
+    if (big) {
+        dim3 grid((g->w + SPB_W - 1) / SPB_W, (g->h + SPB_H - 1) / SPB_H, g->batch), blk(32, 8);
+        if (grid.y <= 65535) {
+            k_splat_big<<<grid, blk, 0, s>>>(density, g->h, g->w, g->pitch_c, g->stride_c, src, off);
+            return check_launch("k_splat_big");
+        }
+    }
+    dim3 grid((g->w + 31) / 32, (g->h + 7) / 8, g->batch), blk(32, 8);
     k_splat<<<grid, blk, 0, s>>>(density, g->h, g->w, g->pitch_c, g->stride_c, src, off);
     return check_launch("k_splat");
 }

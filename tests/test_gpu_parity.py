@@ -82,6 +82,34 @@ def test_units_splat(golden):
     assert nerr(d, g["splat_out"]) < 5e-7
 
 
+@pytest.mark.parametrize("h,w,B,n", [(200, 333, 1, 700), (130, 260, 3, 300), (64, 128, 2, 40), (1024, 1024, 1, 2000)])
+def test_splat_big_tile_kernel_equals_the_small_tile_one(h, w, B, n):
+    """k_splat_big (a CTA owns 128 x 64 cells: big grids with thousands of emitters) against k_splat (32 x 8) bit for bit, and against
+    the oracle's add_smoke_source: overlapping emitters (the sum order matters), emitters across tile edges and outside the grid,
+    lists longer than one 256-entry cull pass, a simulation with no emitter, a non-zero starting density."""
+    rng = np.random.default_rng(h + n)
+    per_sim = []
+    for b in range(B):
+        m = 0 if (B > 1 and b == 1) else n
+        per_sim.append([(int(rng.integers(-5, w + 5)), int(rng.integers(-5, h + 5)), int(rng.integers(1, 14)), float(rng.uniform(0.2, 2.0)))
+                        for _ in range(m)])
+    d0 = rng.uniform(0, 1, (B, h, w)).astype(np.float32)
+    got = {}
+    for big in (0, 1):
+        with smk_env(SMK_SPLAT_BIG=big):
+            ns = make(h, w, batch=B)
+            ns.density = T(d0 if B > 1 else d0[0])
+            ns.add_sources(per_sim)
+            got[big] = N(ns.density).reshape(B, h, w)
+    assert np.array_equal(got[0], got[1])
+    if h * w <= 64 * 1024:
+        for b in range(B):
+            want = d0[b].copy()
+            for x, y, r, i in per_sim[b]:
+                want = oracle.splat(want, x, y, r, i)
+            assert nerr(got[1][b], want) < 5e-7
+
+
 # ------------------------------------------------------------------------------------- whole-step parity
 def test_small_random_steps(golden):
     g = golden("small_random")

@@ -32,11 +32,18 @@ for r in rows:
     elif r[0] == "Function Name":
         pass
     elif r[0].isdigit() and hdr is not None:
-        cur.append((fname.split("/")[-1], int(r[0]), r[1], dict(zip(hdr[4:], r[4:]))))
+        # ncu does not escape quotes inside the source text: take the metric columns from the right
+        nm = len(hdr) - 4
+        if len(r) >= nm + 2:
+            cur.append((fname.split("/")[-1], int(r[0]), ",".join(r[1:len(r) - nm - 2]), dict(zip(hdr[4:], r[-nm:]))))
 if not launches:
     sys.exit("no source page for " + pat)
 L = launches[min(which, len(launches) - 1)]
-f = lambda v: float(v) if v not in ("", "-") else 0.0
+def f(v):
+    try:
+        return float(v)
+    except ValueError:
+        return 0.0
 ti = sum(f(d["Instructions Executed"]) for _, _, _, d in L) or 1
 ts = sum(f(d["# Samples"]) for _, _, _, d in L) or 1
 print("launches on the page: %d; this one: %.0f warp instructions, %.0f samples" % (len(launches), ti, ts))
