@@ -249,6 +249,39 @@ def test_ghost_rows_pushed_ahead_from_the_density_advection(world, H, W, K, halo
             assert_same(N(grp.gather(k))[:, :ref.shape[1]], ref, "%s, second run, world %d, tiled %d" % (k, world, tiled))
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("tiled", [0, 1])
+def test_pushed_ahead_steps_replay_from_a_cuda_graph(tiled):
+    """run_steps inside a stream capture: the side stream of the tail push forks from and joins the capturing stream, the kernels
+    read the exchange number from device memory, programmatic dependent launch is off inside the capture.  Four captured steps
+    (the ping-pong state returns to the same buffers), replayed twice, against the undecomposed run."""
+    from helpers import smk_env
+    world, H, W, K, halo = 3, 300, 260, 12, 18
+    st0 = random_state(H, W, seed=91)
+    with smk_env(SMK_ADVECT_TILED=tiled):
+        grp = LocalGroup((H, W), 0.02, 0.01, "cuda", world=world, jacobi_iters=K, sweeps_per_launch=6, halo=halo, peer=True)
+        whole = NavierStokesSimulator((H, W), 0.02, 0.01, "cuda", jacobi_iters=K, step_kernel="phases")
+        for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+            grp.scatter(k, st0[k])
+            setattr(whole, name, torch.from_numpy(st0[k]).cuda())
+        grp.run_steps(2)                                  # eager first: kernels loaded, side stream and events created
+        torch.cuda.synchronize()
+        before = [(s.local._state.cur_u, s.local._state.cur_v, s.local._state.cur_d, s.local._state.cur_p) for s in grp.slabs]
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            grp.run_steps(4)
+        assert before == [(s.local._state.cur_u, s.local._state.cur_v, s.local._state.cur_d, s.local._state.cur_p) for s in grp.slabs]
+        graph.replay()
+        graph.replay()
+        torch.cuda.synchronize()
+        for _ in range(2 + 8):
+            whole.step()
+        grp.check()
+        for k, name in (("u", "u"), ("v", "v"), ("p", "p"), ("d", "density")):
+            ref = N(getattr(whole, name))
+            assert_same(N(grp.gather(k))[:, :ref.shape[1]], ref, "%s after two replays of a four-step graph, tiled %d" % (k, tiled))
+
+
 def test_fields_cannot_change_while_a_push_is_in_flight():
     a = SlabNavierStokes((300, 260), 0.02, 0.01, "cuda", rank=0, world=1, jacobi_iters=12, sweeps_per_launch=6)
     a._pushed_ahead = True
