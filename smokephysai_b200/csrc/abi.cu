@@ -45,6 +45,7 @@ static void env_read_locked()
     c.project_fused = env_int("SMK_PROJECT_FUSED");
     c.push_stream = env_int("SMK_PUSH_STREAM");
     c.splat_big = env_int("SMK_SPLAT_BIG");
+    c.advect_tma = env_int("SMK_ADVECT_TMA");
     g_env = c;
     g_env_ready.store(1, std::memory_order_release);
 }

@@ -97,6 +97,7 @@ struct EnvCfg {
     int advect_tiled;    // SMK_ADVECT_TILED   0 / 1: direct / shared-memory tiled advection
     int project_fused;   // SMK_PROJECT_FUSED  0: k_project + k_advect(u) as two kernels even where the fused one applies
     int push_stream;     // SMK_PUSH_STREAM    0: the push a slab step issues for the next step stays on the caller's stream
+    int advect_tma;      // SMK_ADVECT_TMA     0: interior tiles of k_advect_tiled stage with cp.async like the others (default: TMA)
     int splat_big;       // SMK_SPLAT_BIG      0 / 1: k_splat / k_splat_big (128 x 64 cells per CTA) whatever the grid size
 };
 const EnvCfg& env();
@@ -131,6 +132,10 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
                   const float* fmul, const smk_slab_check_t* chk, cudaStream_t s, int proj = 0, const float* p = nullptr, float* vout = nullptr,
                   const AdvectPart* part = nullptr);
 bool advect_can_fuse_project(const smk_grid_t* g);
+// 128-byte CUtensorMap of a (pitch, rows, batch) fp32 tensor read / written in box_cols x box_rows x 1 boxes (jacobi.cu); false when
+// the driver entry point is missing or the shape cannot be encoded
+struct alignas(64) TmaMap { unsigned long long opaque[16]; };
+bool tma_map_3d(void* map128, const float* base, int pitch, int rows, int batch, int64_t batch_stride, int box_rows, int box_cols);
 bool advect_is_tiled(const smk_grid_t* g, int rows, int cols);
 int advect_tile_rows();
 int launch_div_norms(const smk_grid_t* g, const float* u, const float* v, float* out, cudaStream_t s);

@@ -507,20 +507,24 @@ static js_encode_fn js_encoder()
     }
     return fn;
 }
-// a (pitch, h, batch) fp32 tensor accessed in box_cols x box_rows x 1 boxes; elements outside it are zero-filled on a load and
-// dropped on a store
-static int js_make_map(CUtensorMap* m, const smk_grid_t* g, const float* base, const int box_rows, const int box_cols = 128)
+// a (pitch, rows, batch) fp32 tensor accessed in box_cols x box_rows x 1 boxes; elements outside it are zero-filled on a load and
+// dropped on a store.  false: no tensor map could be encoded (the caller keeps its non-TMA path).          (common.cuh)
+bool tma_map_3d(void* map128, const float* base, int pitch, int rows, int batch, int64_t batch_stride, int box_rows, int box_cols)
 {
     js_encode_fn enc = js_encoder();
-    if (!enc) return SMK_ENOTMA;
-    const cuuint64_t dims[3] = {(cuuint64_t)g->pitch_c, (cuuint64_t)g->h, (cuuint64_t)g->batch};
+    if (!enc || pitch < 4 || (pitch & 3) || rows < 1 || box_cols > 256 || box_rows > 256 || (box_cols & 3)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
     // the stride of the batch dimension is not used when there is one simulation, but it has to be a valid one
-    const cuuint64_t strides[2] = {(cuuint64_t)g->pitch_c * 4u, (g->batch > 1 ? (cuuint64_t)g->stride_c : (cuuint64_t)g->pitch_c * (cuuint64_t)g->h) * 4u};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4u, (batch > 1 ? (cuuint64_t)batch_stride : (cuuint64_t)pitch * (cuuint64_t)rows) * 4u};
     const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1}, estr[3] = {1, 1, 1};
-    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+    const CUresult r = enc(reinterpret_cast<CUtensorMap*>(map128), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? SMK_OK : SMK_ENOTMA;
+    return r == CUDA_SUCCESS;
+}
+static int js_make_map(CUtensorMap* m, const smk_grid_t* g, const float* base, const int box_rows, const int box_cols = 128)
+{
+    return tma_map_3d(m, base, g->pitch_c, g->h, g->batch, g->stride_c, box_rows, box_cols) ? SMK_OK : SMK_ENOTMA;
 }
 
 template <int NW>

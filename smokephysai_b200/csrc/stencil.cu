@@ -3,6 +3,7 @@
 // stencils or gathers: coalesced row-major access, shared-memory staging with halos where a phase reuses
 // neighbours, no tensor cores (nothing here is a contraction).
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include "common.cuh"
 
@@ -386,6 +387,7 @@ struct AdvectArgs {
     // k_advect_tiled on a part of the tile rows (smk_slab_step computes the rows it sends to its neighbours first): the launch
     // covers tile rows ty0 + blockIdx.y, stepping over the rows [skip_lo[k], skip_lo[k] + skip_n[k]) of up to two bands
     int ty0, skip_lo[2], skip_n[2];
+    int use_tma;                                         // k_advect_tiled: interior tiles stage their windows with TMA box loads
 };
 
 template <bool SLAB>
@@ -493,11 +495,13 @@ constexpr int AT_R = 16, AT_C = 128, AT_HB = 4;
 constexpr int AT_FP = AT_C + 2 * AT_HB, AT_FR = AT_R + 2 * AT_HB;      // staged field window: 24 rows x 136 columns
 constexpr int AT_UP = AT_C + 4, AT_VP = AT_C;                          // u tile 16 x 129 (pitch 132), v tile 17 x 128
 
-struct AdvectTile {
+struct AdvectTile {                                                    // every array starts on a 128-byte boundary (TMA destinations)
     float sF[AT_FR][AT_FP];
     float sU[AT_R][AT_UP];
     float sV[AT_R + 1][AT_VP];
 };
+static_assert(sizeof(float) * AT_FR * AT_FP % 128 == 0 && sizeof(float) * AT_R * AT_UP % 128 == 0 && sizeof(float) * (AT_R + 1) * AT_VP % 128 == 0,
+              "the staged arrays of k_advect_tiled must keep 128-byte offsets");
 
 // ... with the gradient subtract (a7, navier_stokes.py:148-149) fused in: the pressure window behind the staged field window
 // (one more row above for u's p[i-1][j], one more column to the left for v's p[i][j-1]; 16-byte aligned columns)
@@ -512,6 +516,13 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_sr
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ float2 neg2(const float2 a) { return make_float2(-a.x, -a.y); }
+// one box of a (pitch, rows, batch) tensor map -> shared memory, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void at_tma_box(void* smem_dst, const TmaMap* map, const int x, const int y, const int z, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z),
+                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 
 // One value of the advected field straight from global memory (the rare back-trace that leaves the staged window), with the
 // gradient subtract applied on the fly when the kernel fuses it (PROJ 1: the field is u).
@@ -532,7 +543,8 @@ __device__ __forceinline__ float advect_global(const AdvectArgs& a, const float*
 // that let the v advection re-project v from p instead (no Vout) was slower: 274 against 177 us per launch at 8192^2.
 template <bool SLAB, bool INTERIOR, int PROJ>
 __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, float (*sP)[AT_PP], const float* F, const float* U, const float* V,
-                                            const float* P, float* O, const size_t b, const int i0, const int j0)
+                                            const float* P, float* O, const size_t b, const int i0, const int j0,
+                                            const TmaMap* mF, const TmaMap* mU, const TmaMap* mV, const TmaMap* mP, unsigned long long* bar)
 {
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const int w = a.w, rows = a.rows, cols = a.cols, pitch = a.pitch;
@@ -540,6 +552,25 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
     // ---- stage: field window rows [i0-4, i0+20) x columns [j0-4, j0+132), u rows [i0, i0+16), v rows [i0, i0+17) ----
     const int wy0 = INTERIOR ? i0 - AT_HB : max(i0 - AT_HB, 0), wy1 = INTERIOR ? i0 + AT_R + AT_HB : min(i0 + AT_R + AT_HB, rows);
     const int wx0 = INTERIOR ? j0 - AT_HB : max(j0 - AT_HB, 0), wx1 = INTERIOR ? j0 + AT_C + AT_HB : min(j0 + AT_C + AT_HB, pitch);
+    if (INTERIOR && a.use_tma) {
+        // interior tile, TMA staging: the same windows as three box loads (four with the pressure window) issued by ONE thread --
+        // no per-thread address arithmetic, no LDGSTS through the LSU pipe; every thread then waits on the mbarrier they complete on
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            constexpr unsigned BYTES = sizeof(float) * (AT_FR * AT_FP + (AT_R + 1) * AT_VP + (PROJ ? AT_PR * AT_PP : AT_R * AT_UP));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(BYTES) : "memory");
+            at_tma_box(&T.sF[0][0], mF, j0 - AT_HB, i0 - AT_HB, (int)b, bar);
+            at_tma_box(&T.sV[0][0], mV, j0, i0, (int)b, bar);
+            if (PROJ) at_tma_box(&sP[0][0], mP, j0 - 8, i0 - AT_HB - 1, (int)b, bar);
+            else      at_tma_box(&T.sU[0][0], mU, j0, i0, (int)b, bar);
+        }
+        __syncthreads();                                                   // the barrier is initialised and armed
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(0u) : "memory");
+    } else {
 #pragma unroll
     for (int rr = 0; rr < AT_FR / 8; ++rr) {                         // warp wp copies window rows wp, wp+8, wp+16
         const int r = wp + 8 * rr, y = i0 - AT_HB + r;
@@ -584,6 +615,7 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    }
     if (PROJ && INTERIOR) {
         // every staged cell is one k_project updates: four cells per LDS.128 / STS.128, no predicate
         const float dt = a.dt;
@@ -794,10 +826,12 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
 
 template <bool SLAB, int PROJ>
 __global__ void __launch_bounds__(256, PROJ ? 5 : 6)        // 40 registers: 6 CTAs per SM beat 4 (62 registers) by 12 % and 7 (32, spills) by 5 %; the pressure window of the fused variants leaves room for 5
-k_advect_tiled(const AdvectArgs a)
+k_advect_tiled(const AdvectArgs a, const __grid_constant__ TmaMap mF, const __grid_constant__ TmaMap mU, const __grid_constant__ TmaMap mV,
+               const __grid_constant__ TmaMap mP)
 {
     pdl_prologue();
-    __shared__ __align__(16) typename std::conditional<PROJ != 0, AdvectTileP, AdvectTile>::type TT;
+    __shared__ __align__(128) typename std::conditional<PROJ != 0, AdvectTileP, AdvectTile>::type TT;
+    __shared__ __align__(8) unsigned long long tma_bar;
     AdvectTile& T = *reinterpret_cast<AdvectTile*>(&TT);
     float (*sP)[AT_PP] = PROJ ? reinterpret_cast<float (*)[AT_PP]>(reinterpret_cast<char*>(&TT) + sizeof(AdvectTile)) : nullptr;
     int ty = (int)blockIdx.y + a.ty0;
@@ -828,8 +862,8 @@ k_advect_tiled(const AdvectArgs a)
     if (SLAB && a.overflow)
         interior = interior && ((i0 - AT_HB >= a.valid_lo && i0 + AT_R + AT_HB <= a.valid_hi) || i0 + AT_R <= a.need_lo || i0 >= a.need_hi);
     if (PROJ) interior = interior && i0 >= AT_HB + 1 && i0 + AT_R + AT_HB <= a.h && j0 >= 8 && j0 + AT_C + 8 <= a.pc && j0 + AT_C + AT_HB <= a.w;
-    if (interior) advect_tile<SLAB, true, PROJ>(a, T, sP, F, U, V, P, O, b, i0, j0);
-    else          advect_tile<SLAB, false, PROJ>(a, T, sP, F, U, V, P, O, b, i0, j0);
+    if (interior) advect_tile<SLAB, true, PROJ>(a, T, sP, F, U, V, P, O, b, i0, j0, &mF, &mU, &mV, &mP, &tma_bar);
+    else          advect_tile<SLAB, false, PROJ>(a, T, sP, F, U, V, P, O, b, i0, j0, &mF, &mU, &mV, &mP, &tma_bar);
 }
 
 // proj / p / vout: 0 / NULL / NULL for the plain advection; 1 fuses the gradient subtract of the pressure p into the tiled u
@@ -873,6 +907,19 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
     a.valid_lo = chk ? chk->valid_lo : 0; a.valid_hi = chk ? chk->valid_hi : 0; a.overflow = chk ? chk->overflow_flag : nullptr;
     a.P = p; a.pc = g->pitch_c; a.sc_ = g->stride_c; a.Vout = vout;
     a.ty0 = 0; a.skip_lo[0] = a.skip_lo[1] = 0x7fffffff; a.skip_n[0] = a.skip_n[1] = 0;
+    a.use_tma = 0;
+    TmaMap mF, mU, mV, mP;
+    memset(&mF, 0, sizeof mF); memset(&mU, 0, sizeof mU); memset(&mV, 0, sizeof mV); memset(&mP, 0, sizeof mP);
+    // tensor maps for the tiled kernel's interior tiles (SMK_ADVECT_TMA=0: cp.async staging everywhere); any failure keeps cp.async
+    auto make_maps = [&]() {
+        if (env().advect_tma == 0) return;
+        const int urows = g->h + 1;
+        bool ok = tma_map_3d(&mF, field, pitch, rows, g->batch, stride, AT_FR, AT_FP) &&
+                  tma_map_3d(&mV, v, g->pitch_v, g->h, g->batch, g->stride_v, AT_R + 1, AT_VP);
+        if (ok && proj) ok = tma_map_3d(&mP, p, g->pitch_c, g->h, g->batch, g->stride_c, AT_PR, AT_PP);
+        if (ok && !proj) ok = tma_map_3d(&mU, u, g->pitch_u, urows, g->batch, g->stride_u, AT_R, AT_UP);
+        a.use_tma = ok ? 1 : 0;
+    };
     const unsigned long long nthreads = (unsigned long long)rows * a.ngroups;
     dim3 grid((unsigned)((nthreads + 255) / 256), g->batch);
     if (proj) {
@@ -881,8 +928,9 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
         ProfScope prof_(SMK_PH_PROJECT_ADVECT_U, s);
         dim3 tgrid((unsigned)((pitch + AT_C - 1) / AT_C), (unsigned)((rows + AT_R - 1) / AT_R), g->batch);
         const bool slab_ = g->gh != 0 && (g->gh != g->h || g->row0 != 0);
-        if (slab_) launch_chain(k_advect_tiled<true, 1>, tgrid, dim3(256), 0, s, a);
-        else       launch_chain(k_advect_tiled<false, 1>, tgrid, dim3(256), 0, s, a);
+        make_maps();
+        if (slab_) launch_chain(k_advect_tiled<true, 1>, tgrid, dim3(256), 0, s, a, mF, mU, mV, mP);
+        else       launch_chain(k_advect_tiled<false, 1>, tgrid, dim3(256), 0, s, a, mF, mU, mV, mP);
         return check_launch("k_advect_tiled (fused gradient subtract)");
     }
     ProfScope prof_(rows == g->h + 1 ? SMK_PH_ADVECT_U : (cols == g->w + 1 ? SMK_PH_ADVECT_V : SMK_PH_ADVECT_D), s);
@@ -903,8 +951,9 @@ int launch_advect(const smk_grid_t* g, const float* field, float* out, int rows,
             if (ny <= 0) return SMK_OK;
             tgrid.y = (unsigned)ny;
         }
-        if (slab) launch_chain(k_advect_tiled<true, 0>, tgrid, dim3(256), 0, s, a);
-        else      launch_chain(k_advect_tiled<false, 0>, tgrid, dim3(256), 0, s, a);
+        make_maps();
+        if (slab) launch_chain(k_advect_tiled<true, 0>, tgrid, dim3(256), 0, s, a, mF, mU, mV, mP);
+        else      launch_chain(k_advect_tiled<false, 0>, tgrid, dim3(256), 0, s, a, mF, mU, mV, mP);
         return check_launch("k_advect_tiled");
     }
     if (part) return fail(SMK_EUNSUPPORTED, "launch_advect: a part of the rows needs the tiled kernel (advect_is_tiled)");

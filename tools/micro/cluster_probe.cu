@@ -10,7 +10,7 @@ namespace smk {
 int fail(int c, const char*, ...) { return c; }
 int check_launch(const char*) { return 0; }
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-static EnvCfg g_env_probe = {SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET};
+static EnvCfg g_env_probe = {SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET, SMK_ENV_UNSET};
 const EnvCfg& env() { return g_env_probe; }
 void prof_mark(int, cudaStream_t, bool) {}
 }
