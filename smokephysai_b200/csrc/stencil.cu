@@ -61,15 +61,40 @@ __device__ __forceinline__ void st4_partial(float* p, const float4 v, int n)
 // once with cp.async and awaited once -- the generic path's LDG -> STS loop serialises six DRAM round trips per warp,
 // which is what bound the kernel (long-scoreboard stalls, 44 % of DRAM peak) -- and the buoyancy is then added in
 // shared memory by the thread that copied the chunk.
+// one box of a (pitch, rows, batch) tensor map -> shared memory, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void at_tma_box(void* smem_dst, const TmaMap* map, const int x, const int y, const int z, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z),
+                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// thread 0 of a CTA: initialise the mbarrier and arm it for `bytes` of TMA traffic
+__device__ __forceinline__ void tma_bar_arm(unsigned long long* bar, const unsigned bytes)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bar_wait(unsigned long long* bar, const unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ void fdd_cp_async16(float* smem_dst, const float* gmem_src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 
-struct FddTile {
+struct FddTile {                // su, sv, sd start on 128-byte boundaries (TMA destinations of the interior tiles)
     float su[FTH + 3][FSP];     // u rows i0-1 .. i0+FTH+1
+    float pad0[(128 - sizeof(float) * (FTH + 3) * FSP % 128) % 128 / sizeof(float)];
     float sv[FTH + 2][FSP];     // v + buoyancy, rows i0-1 .. i0+FTH
+    float pad1[(128 - sizeof(float) * (FTH + 2) * FSP % 128) % 128 / sizeof(float)];
     float sd[FTH + 2][FSP];     // density, same rows
+    float pad2[(128 - sizeof(float) * (FTH + 2) * FSP % 128) % 128 / sizeof(float)];
     float su1[FTH + 1][FTW];    // diffused u, rows i0 .. i0+FTH
     float sv1[FTH][FTW + 4];    // diffused v, cols j0 .. j0+128
 };
@@ -78,7 +103,8 @@ template <bool INTERIOR>
 __device__ __forceinline__ void fdd_tile(FddTile& T, const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ D,
                                          float* __restrict__ Uo, float* __restrict__ Vo, float* __restrict__ Do, float* __restrict__ DIV,
                                          const int h, const int w, const int pu, const int pv, const int pc,
-                                         const float dt, const float c_uv, const float c_d, const int i0, const int j0)
+                                         const float dt, const float c_uv, const float c_d, const int i0, const int j0,
+                                         const int b, const TmaMap* mU, const TmaMap* mV, const TmaMap* mD, unsigned long long* bar)
 {
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const int c0 = j0 + 4 * lane;                  // first global column of this lane's float4
@@ -87,6 +113,18 @@ __device__ __forceinline__ void fdd_tile(FddTile& T, const float* __restrict__ U
     if (INTERIOR) {
         // shared column c holds global column j0 - 4 + c: whole 16-byte chunks [j0-4, j0+132) of every staged row
         constexpr int NCH = FSP / 4;               // 34 chunks per row
+        if (bar) {
+            // TMA: the three windows as three box loads issued by one thread (round 2; the 1870 LDGSTS of the path below and their
+            // address arithmetic were ~13 % of the kernel's instructions)
+            if (threadIdx.x == 0) {
+                tma_bar_arm(bar, sizeof(float) * ((FTH + 3) + 2 * (FTH + 2)) * FSP);
+                at_tma_box(&T.su[0][0], mU, j0 - 4, i0 - 1, b, bar);
+                at_tma_box(&T.sv[0][0], mV, j0 - 4, i0 - 1, b, bar);
+                at_tma_box(&T.sd[0][0], mD, j0 - 4, i0 - 1, b, bar);
+            }
+            __syncthreads();
+            tma_bar_wait(bar, 0u);
+        } else {
         for (int k = threadIdx.x; k < (FTH + 3) * NCH; k += FTHREADS) {
             const int r = k / NCH, c = (k - r * NCH) * 4;
             fdd_cp_async16(&T.su[r][c], U + ((size_t)(i0 - 1 + r) * pu + (j0 - 4 + c)));
@@ -98,7 +136,9 @@ __device__ __forceinline__ void fdd_tile(FddTile& T, const float* __restrict__ U
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        // buoyancy: v[:, :-1] += dt * (density * 0.1) (navier_stokes.py:154-155) on the chunks this thread copied
+        }
+        // buoyancy: v[:, :-1] += dt * (density * 0.1) (navier_stokes.py:154-155) on the chunks this thread copied (cp.async: a thread
+        // sees its own copies after wait_group; TMA: every thread sees everything after the mbarrier)
         for (int k = threadIdx.x; k < (FTH + 2) * NCH; k += FTHREADS) {
             const int r = k / NCH, c = (k - r * NCH) * 4;
             float4 x = lds4(&T.sv[r][c]);
@@ -206,10 +246,12 @@ k_forces_diffuse_div(const float* __restrict__ U, const float* __restrict__ V, c
                      float* __restrict__ Uo, float* __restrict__ Vo, float* __restrict__ Do, float* __restrict__ DIV,
                      const int h, const int w, const int pu, const int pv, const int pc,
                      const long long su_, const long long sv_, const long long sc_,
-                     const float dt, const float c_uv, const float c_d, const int bulk)
+                     const float dt, const float c_uv, const float c_d, const int bulk,
+                     const __grid_constant__ TmaMap mU, const __grid_constant__ TmaMap mV, const __grid_constant__ TmaMap mD)
 {
     pdl_prologue();
-    __shared__ __align__(16) FddTile T;
+    __shared__ __align__(128) FddTile T;
+    __shared__ __align__(8) unsigned long long tma_bar;
     const int i0 = blockIdx.y * FTH, j0 = blockIdx.x * FTW;
     const size_t b = blockIdx.z;
     U += b * su_; Uo += b * su_; V += b * sv_; Vo += b * sv_; D += b * sc_; Do += b * sc_;
@@ -219,8 +261,9 @@ k_forces_diffuse_div(const float* __restrict__ U, const float* __restrict__ V, c
     // (bulk: only on grids of several CTA waves -- on small ones the extra shared-memory pass of the buoyancy costs more
     // latency than the serialised loads: 16.1 against 14.2 us at 1024^2, 334 against 446 us at 8192^2)
     const bool interior = bulk && i0 >= 1 && i0 + FTH + 1 <= h - 1 && j0 >= 4 && j0 + FTW + 4 <= w && j0 + FTW + 4 <= pu && j0 + FTW + 4 <= pc;
-    if (interior) fdd_tile<true>(T, U, V, D, Uo, Vo, Do, DIV, h, w, pu, pv, pc, dt, c_uv, c_d, i0, j0);
-    else          fdd_tile<false>(T, U, V, D, Uo, Vo, Do, DIV, h, w, pu, pv, pc, dt, c_uv, c_d, i0, j0);
+    // bulk == 2: interior tiles stage by TMA
+    if (interior) fdd_tile<true>(T, U, V, D, Uo, Vo, Do, DIV, h, w, pu, pv, pc, dt, c_uv, c_d, i0, j0, (int)b, &mU, &mV, &mD, bulk == 2 ? &tma_bar : nullptr);
+    else          fdd_tile<false>(T, U, V, D, Uo, Vo, Do, DIV, h, w, pu, pv, pc, dt, c_uv, c_d, i0, j0, (int)b, &mU, &mV, &mD, nullptr);
 }
 
 int launch_forces_diffuse_div(const smk_grid_t* g, const float* u, const float* v, const float* d,
@@ -229,9 +272,16 @@ int launch_forces_diffuse_div(const smk_grid_t* g, const float* u, const float* 
     dim3 grid((g->w + FTW - 1) / FTW, (g->h + FTH - 1) / FTH, g->batch);
     ProfScope prof_(SMK_PH_FORCES_DIFFUSE_DIV, s);
     int bulk = (int64_t)g->h * g->w * g->batch >= ((int64_t)6 << 20) ? 1 : 0;
-    if (env().fdd_bulk != SMK_ENV_UNSET) bulk = env().fdd_bulk != 0;       // tests force either staging path on small grids
+    if (env().fdd_bulk != SMK_ENV_UNSET) bulk = env().fdd_bulk;             // tests force a staging path on small grids: 0 / 1 (cp.async) / 2 (TMA)
+    else if (bulk) bulk = 2;
+    TmaMap mU, mV, mD;
+    memset(&mU, 0, sizeof mU); memset(&mV, 0, sizeof mV); memset(&mD, 0, sizeof mD);
+    if (bulk == 2 && !(tma_map_3d(&mU, u, g->pitch_u, g->h + 1, g->batch, g->stride_u, FTH + 3, FSP) &&
+                       tma_map_3d(&mV, v, g->pitch_v, g->h, g->batch, g->stride_v, FTH + 2, FSP) &&
+                       tma_map_3d(&mD, d, g->pitch_c, g->h, g->batch, g->stride_c, FTH + 2, FSP)))
+        bulk = 1;                                                            // no tensor map: cp.async
     launch_chain(k_forces_diffuse_div, grid, dim3(FTHREADS), 0, s, u, v, d, uo, vo, dout, div, g->h, g->w, g->pitch_u, g->pitch_v, g->pitch_c,
-                                                   g->stride_u, g->stride_v, g->stride_c, dt, c_uv, c_d, bulk);
+                                                   g->stride_u, g->stride_v, g->stride_c, dt, c_uv, c_d, bulk, mU, mV, mD);
     return check_launch("k_forces_diffuse_div");
 }
 
@@ -516,13 +566,7 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_sr
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ float2 neg2(const float2 a) { return make_float2(-a.x, -a.y); }
-// one box of a (pitch, rows, batch) tensor map -> shared memory, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void at_tma_box(void* smem_dst, const TmaMap* map, const int x, const int y, const int z, unsigned long long* bar)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z),
-                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
+
 
 // One value of the advected field straight from global memory (the rare back-trace that leaves the staged window), with the
 // gradient subtract applied on the fly when the kernel fuses it (PROJ 1: the field is u).
@@ -556,20 +600,14 @@ __device__ __forceinline__ void advect_tile(const AdvectArgs& a, AdvectTile& T, 
         // interior tile, TMA staging: the same windows as three box loads (four with the pressure window) issued by ONE thread --
         // no per-thread address arithmetic, no LDGSTS through the LSU pipe; every thread then waits on the mbarrier they complete on
         if (tid == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            constexpr unsigned BYTES = sizeof(float) * (AT_FR * AT_FP + (AT_R + 1) * AT_VP + (PROJ ? AT_PR * AT_PP : AT_R * AT_UP));
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(BYTES) : "memory");
+            tma_bar_arm(bar, sizeof(float) * (AT_FR * AT_FP + (AT_R + 1) * AT_VP + (PROJ ? AT_PR * AT_PP : AT_R * AT_UP)));
             at_tma_box(&T.sF[0][0], mF, j0 - AT_HB, i0 - AT_HB, (int)b, bar);
             at_tma_box(&T.sV[0][0], mV, j0, i0, (int)b, bar);
             if (PROJ) at_tma_box(&sP[0][0], mP, j0 - 8, i0 - AT_HB - 1, (int)b, bar);
             else      at_tma_box(&T.sU[0][0], mU, j0, i0, (int)b, bar);
         }
         __syncthreads();                                                   // the barrier is initialised and armed
-        unsigned done = 0;
-        while (!done)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(0u) : "memory");
+        tma_bar_wait(bar, 0u);
     } else {
 #pragma unroll
     for (int rr = 0; rr < AT_FR / 8; ++rr) {                         // warp wp copies window rows wp, wp+8, wp+16

@@ -529,11 +529,12 @@ def test_both_advection_kernels_in_slabs(force_advect_kernel, tiled):
         assert_same(N(grp.gather(k))[:, :st0[k].shape[1]], N(getattr(whole, name)), "%s tiled %d" % (k, tiled))
 
 
-@pytest.mark.parametrize("bulk", [0, 1])
+@pytest.mark.parametrize("bulk", [0, 1, 2])
 @pytest.mark.parametrize("h,w", [(100, 400), (64, 300), (35, 260), (130, 1000), (48, 392)])
 def test_both_staging_paths_of_forces_diffuse_div_vs_oracle(bulk, h, w):
-    """k_forces_diffuse_div stages interior tiles with bulk cp.async copies on big grids (SMK_FDD_BULK forces it): both
-    paths, on grids that have interior AND edge tiles, against the oracle, bit for bit."""
+    """k_forces_diffuse_div stages interior tiles of big grids with bulk cp.async copies (SMK_FDD_BULK=1) or three TMA box loads
+    (=2, the default there); 0 is the LDG -> STS path of small grids and edge tiles.  All three, on grids that have interior AND
+    edge tiles, against the oracle, bit for bit."""
     with smk_env(SMK_FDD_BULK=bulk):
         rng = np.random.default_rng(h + w + bulk)
         ref = oracle.OracleSolver((h, w), 0.02, 0.01, 5)
