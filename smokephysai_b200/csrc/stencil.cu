@@ -1028,6 +1028,8 @@ k_splat(float* __restrict__ Dn, const int h, const int w, const int pc, const lo
             const long long r = e.radius;
             hit = (long long)j0 <= e.x + r && (long long)j0 + 31 >= e.x - r && (long long)i0 <= e.y + r && (long long)i0 + 7 >= e.y - r;
         }
+        // most 256-emitter chunks of a long list miss the tile altogether: one barrier-with-vote, and on to the next chunk
+        if (!__syncthreads_or(hit ? 1 : 0)) continue;
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (lane == 0) wcount[wp] = __popc(m);
         __syncthreads();
@@ -1079,6 +1081,8 @@ k_splat_big(float* __restrict__ Dn, const int h, const int w, const int pc, cons
             const long long r = e.radius;
             hit = (long long)j0 <= e.x + r && (long long)j0 + (SPB_W - 1) >= e.x - r && (long long)i0 <= e.y + r && (long long)i0 + (SPB_H - 1) >= e.y - r;
         }
+        // most 256-emitter chunks of a long list miss the tile altogether: one barrier-with-vote, and on to the next chunk
+        if (!__syncthreads_or(hit ? 1 : 0)) continue;
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (lane == 0) wcount[wp] = __popc(m);
         __syncthreads();

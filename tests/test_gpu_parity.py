@@ -473,6 +473,7 @@ def force_advect_kernel():
         os.environ["SMK_ADVECT_TILED"] = str(v)
         _lib.reload_env()
     yield set_
+    os.environ.pop("SMK_ADVECT_TMA", None)
     if old is None:
         os.environ.pop("SMK_ADVECT_TILED", None)
     else:
@@ -480,13 +481,18 @@ def force_advect_kernel():
     _lib.reload_env()
 
 
-@pytest.mark.parametrize("tiled", [0, 1])
+@pytest.mark.parametrize("tiled", [0, 1, 2])
 @pytest.mark.parametrize("h,w,K", [(1, 1, 2), (3, 3, 2), (5, 131, 3), (131, 5, 3), (129, 129, 4), (130, 260, 4), (300, 200, 3),
                                    (257, 383, 3), (16, 128, 2), (17, 132, 2), (40, 300, 2), (64, 1000, 2)])
 def test_both_advection_kernels_vs_oracle(force_advect_kernel, tiled, h, w, K):
     """Phase-per-kernel step with each advection kernel forced, on ragged grids with back-traces of up to 3 cells (inside
-    the tiled kernel's staged window) and of up to 12 cells (its global fallback), against the oracle, bit for bit."""
-    force_advect_kernel(tiled)
+    the tiled kernel's staged window) and of up to 12 cells (its global fallback), against the oracle, bit for bit.
+    tiled: 0 the direct kernel, 1 the tiled one (interior tiles staged by TMA box loads), 2 the tiled one with cp.async staging
+    everywhere (SMK_ADVECT_TMA=0)."""
+    force_advect_kernel(min(tiled, 1))
+    if tiled == 2:
+        os.environ["SMK_ADVECT_TMA"] = "0"
+        _lib.reload_env()
     for vel in (300.0, 1200.0):
         rng = np.random.default_rng(h * 1000 + w + int(vel))
         ref = oracle.OracleSolver((h, w), 0.02, 0.01, K)
