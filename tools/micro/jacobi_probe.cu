@@ -9,7 +9,10 @@ namespace smk { int fail(int c, const char*, ...) { return c; } int check_launch
 using namespace smk;
 
 // DBG bit 0: no shuffles, bit 1: no CTA barrier, bit 2: no halo LDS/STS, bit 3: no FP (only exchange)
-template <int PMASK, int DBG, int NW, int IFIRST = 0>
+// STAG: 0 every warp runs the sweep in the same order (IFIRST); else two groups of warps run different orders, so that the shuffle /
+// halo part of one group overlaps the arithmetic of the other: 1: (warp >> 2) & 1 picks ORDER 1 / 0 (two warps of each group on every
+// scheduler), 2: warp & 1 (whole schedulers), 3: (warp >> 2) & 1 picks ORDER 2 / 1, 4: (warp >> 2) & 1 picks ORDER 2 / 0
+template <int PMASK, int DBG, int NW, int IFIRST = 0, int STAG = 0>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_probe(const float* __restrict__ pin, float* __restrict__ pout, const float* __restrict__ div, const int T)
 {
@@ -46,8 +49,20 @@ k_probe(const float* __restrict__ pin, float* __restrict__ pout, const float* __
             }
             float4* pf = (DBG & 4) ? nullptr : &halo[half ^ 1][0][warp][lane];
             float4* pl = (DBG & 4) ? nullptr : &halo[half ^ 1][1][warp][lane];
-            if (half == 0) sweep_packed<PMASK, DBG, false, IFIRST>(A, B, ND, up, dn, M, ringmask, pf, pl);
-            else           sweep_packed<PMASK, DBG, false, IFIRST>(B, A, ND, up, dn, M, ringmask, pf, pl);
+            if (STAG == 0) {
+                if (half == 0) sweep_packed<PMASK, DBG, false, IFIRST>(A, B, ND, up, dn, M, ringmask, pf, pl);
+                else           sweep_packed<PMASK, DBG, false, IFIRST>(B, A, ND, up, dn, M, ringmask, pf, pl);
+            } else {
+                constexpr int OA = (STAG == 3 || STAG == 4) ? 2 : 1, OB = STAG == 3 ? 1 : 0;
+                const bool grp = STAG == 2 ? (warp & 1) : ((warp >> 2) & 1);
+                if (grp) {
+                    if (half == 0) sweep_packed<PMASK, DBG, false, OA>(A, B, ND, up, dn, M, ringmask, pf, pl);
+                    else           sweep_packed<PMASK, DBG, false, OA>(B, A, ND, up, dn, M, ringmask, pf, pl);
+                } else {
+                    if (half == 0) sweep_packed<PMASK, DBG, false, OB>(A, B, ND, up, dn, M, ringmask, pf, pl);
+                    else           sweep_packed<PMASK, DBG, false, OB>(B, A, ND, up, dn, M, ringmask, pf, pl);
+                }
+            }
             if (!(DBG & 2)) __syncthreads();
         }
     }
@@ -134,7 +149,7 @@ void run_desync(const char* name, float* p, float* q, float* d, int nb)
     printf("%-64s %7.4f us/sweep  (%5.0f cycles at 1965 MHz)  %s\n", name, us_per_sweep, us_per_sweep * 1965, cudaGetErrorString(cudaGetLastError()));
 }
 
-template <int PMASK, int DBG, int IFIRST = 0>
+template <int PMASK, int DBG, int IFIRST = 0, int STAG = 0>
 void run(const char* name, float* p, float* q, float* d, int nb)
 {
     cudaEvent_t e0, e1;
@@ -142,10 +157,10 @@ void run(const char* name, float* p, float* q, float* d, int nb)
     float ms[2];
     const int Ts[2] = {200, 1000};
     for (int k = 0; k < 2; ++k) {
-        k_probe<PMASK, DBG, 16, IFIRST><<<nb, 512>>>(p, q, d, Ts[k]);
+        k_probe<PMASK, DBG, 16, IFIRST, STAG><<<nb, 512>>>(p, q, d, Ts[k]);
         cudaDeviceSynchronize();
         cudaEventRecord(e0);
-        k_probe<PMASK, DBG, 16, IFIRST><<<nb, 512>>>(p, q, d, Ts[k]);
+        k_probe<PMASK, DBG, 16, IFIRST, STAG><<<nb, 512>>>(p, q, d, Ts[k]);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         cudaEventElapsedTime(&ms[k], e0, e1);
@@ -162,6 +177,13 @@ int main()
     float *p, *q, *d;
     cudaMalloc(&p, n * 4); cudaMalloc(&q, n * 4); cudaMalloc(&d, n * 4);
     cudaMemset(p, 0, n * 4); cudaMemset(d, 0, n * 4);
+    run<6, 0, 0, 1>("half packed, staggered: warp groups of 4 alternate interior-first / boundary-first", p, q, d, sms);
+    run<7, 0, 0, 1>("mask 7, staggered: warp groups of 4 alternate interior-first / boundary-first", p, q, d, sms);
+    run<15, 0, 0, 1>("packed, staggered: warp groups of 4 alternate interior-first / boundary-first", p, q, d, sms);
+    run<6, 0, 0, 2>("half packed, staggered by warp parity (whole schedulers)", p, q, d, sms);
+    run<6, 0, 0, 3>("half packed, staggered: groups of 4 alternate order 2 / order 1", p, q, d, sms);
+    run<6, 0, 0, 4>("half packed, staggered: groups of 4 alternate order 2 / order 0", p, q, d, sms);
+    run<7, 0, 0, 3>("mask 7, staggered: groups of 4 alternate order 2 / order 1", p, q, d, sms);
     run_desync<16>("scalar, neighbour mbarriers instead of the CTA barrier", p, q, d, sms);
     run_desync<6>("half packed, neighbour mbarriers", p, q, d, sms);
     run_desync<15>("packed, neighbour mbarriers", p, q, d, sms);
