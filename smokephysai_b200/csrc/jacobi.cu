@@ -634,14 +634,16 @@ int launch_jacobi(const smk_grid_t* g, const float* div, float* p, float* scratc
     if (tile == 0) {
         // Many waves of CTAs (>= 4 per SM: 4096^2, or a 1/8 slab of 8192^2): overlap one tile's load / store with another's sweeps.
         // Without the TMA kernel: 64 x 128 tiles at two CTAs per SM (7-8 % faster than 128 x 128 tiles at 4096^2 and 8192^2, equal
-        // at 2048^2: tools/tune_jacobi.py).  With it: persistent CTAs that prefetch their next tile, 128 x 128 when the grid
-        // has many tile rows (another 6-10 %), 64 x 128 x 2 for slab-shaped grids (table above).
+        // at 2048^2: tools/tune_jacobi.py).  With it: persistent CTAs on 128 x 128 tiles that prefetch their next tile and store by
+        // TMA, from 8 tile rows on (tools/tune_jacobi_stream.py after the TMA store, us per 20 sweeps of an h x 8192 slab, streaming
+        // 128 x 128 / streaming 64 x 128 x 2 / plain 64 x 128 x 2: h = 560: 51 / 59 / 48, 1072: 93 / 95 / 92, 1600: 129 / 131 / 135,
+        // 2096: 155 / 168 / 174); shorter grids keep the plain two-CTAs-per-SM kernel.
         const long ctas128 = (long)ntiles(g->w, 128, 12) * ntiles(g->h, 128, 10) * g->batch;
         if (ctas128 >= 4L * sm_count()) {
             tile = 1;
-            if (stream < 0 && use_packed() != 0 && g->pitch_c >= 128 && js_encoder() != nullptr) {
+            if (stream < 0 && use_packed() != 0 && g->pitch_c >= 128 && js_encoder() != nullptr && ntiles(g->h, 128, 10) >= 8) {
                 stream = 2;
-                if (ntiles(g->h, 128, 10) >= 16) tile = 2;
+                tile = 2;
             }
         }
     }
